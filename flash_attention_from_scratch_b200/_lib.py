@@ -1,0 +1,71 @@
+"""ctypes binding of libfa_sm100.so (C ABI: include/fa_sm100.h).
+
+There is deliberately NO fallback: if the shared library is missing or fails to load the
+import of the operator raises, so a GPU box can never silently run something else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# FA_SM100_LIB selects another build of the SAME library (e.g. the hang-guard bring-up build).
+LIB_PATH = Path(os.environ.get("FA_SM100_LIB", str(_DEFAULT_LIB_PATH)))
+
+FA_DTYPE_FP16 = 5
+FA_DTYPE_BF16 = 15
+
+# name -> (restype, argtypes); must list every symbol include/fa_sm100.h declares
+_P, _I, _L = C.c_void_p, C.c_int, C.c_int64
+_FWD_ARGS = [_P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I]
+SYMBOLS = {
+    "fa_fwd": (_I, _FWD_ARGS + [_P]),
+    "fa_fwd_timed": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_float)]),
+    "fa_fwd_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "fa_host_workspace_free": (_I, [_I]),
+    "fa_last_error_string": (C.c_char_p, []),
+    "fa_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
+    "fa_launch_count": (_L, []),
+    "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32)]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the shared library. Raises RuntimeError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is not built; run `python -m flash_attention_from_scratch_b200.build` "
+                "(there is no fallback implementation)"
+            )
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().fa_last_error_string().decode("utf-8", "replace")
+
+
+def launch_count() -> int:
+    return int(load().fa_launch_count())
+
+
+def kernel_info() -> dict:
+    v = [C.c_int() for _ in range(4)]
+    load().fa_kernel_info(*[C.byref(x) for x in v])
+    return dict(zip(("smem_bytes", "threads", "rows_per_cta", "tmem_cols"), (x.value for x in v)))

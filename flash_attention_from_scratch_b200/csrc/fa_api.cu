@@ -1,0 +1,398 @@
+// Host side of libfa_sm100.so: argument checks, TMA tensor-map construction, launch.
+// C ABI declared in include/fa_sm100.h.  Replaces the reference's pybind11 launcher
+// (/root/reference/src/flash_attention.cu:34-149); links only cudart (the one driver symbol,
+// cuTensorMapEncodeTiled, is resolved at run time through cudaGetDriverEntryPoint so the library
+// loads on machines without libcuda).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fa_sm100.h"
+#include "fa_fwd_sm100.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define FA_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return fail(FA_ERR_LAUNCH, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static std::once_flag once;
+    static EncodeTiledFn fn = nullptr;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    });
+    return fn;
+}
+
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    std::once_flag once;
+    int status = FA_OK;
+    int n_sms = 0;
+    int smem_optin = 0;
+    int cc = 0;
+    char err[256] = "";
+};
+DeviceState g_dev[kMaxDevices];
+
+template <bool kBF16, bool kDebug>
+cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(fa::fa_fwd_kernel<kBF16, kDebug>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
+}
+
+// One-time per-device setup: capability check + opt-in dynamic shared memory
+// (the reference does the latter at module import, flash_attention.cu:142-149).
+int init_device(int dev) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(FA_ERR_DEVICE, "bad device index %d", dev);
+    DeviceState& st = g_dev[dev];
+    std::call_once(st.once, [&] {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) {
+            st.status = FA_ERR_DEVICE;
+            snprintf(st.err, sizeof(st.err), "cudaGetDeviceProperties(%d): %s", dev,
+                     cudaGetErrorString(e));
+            return;
+        }
+        st.n_sms = prop.multiProcessorCount;
+        st.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+        st.cc = prop.major * 10 + prop.minor;
+        if (prop.major != 10) {
+            st.status = FA_ERR_DEVICE;
+            snprintf(st.err, sizeof(st.err),
+                     "Flash Attention (B200 build) requires SM_100 (current: SM_%d.%d)", prop.major,
+                     prop.minor);
+            return;
+        }
+        if (st.smem_optin < fa::kSmemLaunchBytes) {
+            st.status = FA_ERR_DEVICE;
+            snprintf(st.err, sizeof(st.err), "device offers %d B opt-in shared memory, need %d",
+                     st.smem_optin, fa::kSmemLaunchBytes);
+            return;
+        }
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
+        e = set_smem_attr<true, false>();
+        if (e == cudaSuccess) e = set_smem_attr<false, false>();
+        if (e == cudaSuccess) e = set_smem_attr<true, true>();
+        if (e == cudaSuccess) e = set_smem_attr<false, true>();
+        if (cur != dev && cur >= 0) cudaSetDevice(cur);
+        if (e != cudaSuccess) {
+            st.status = FA_ERR_LAUNCH;
+            snprintf(st.err, sizeof(st.err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+    });
+    if (st.status != FA_OK) return fail(st.status, "%s", st.err);
+    return FA_OK;
+}
+
+struct Problem {
+    const void *q, *k, *v;
+    void* o;
+    int B, N, H;
+    int64_t sb, sn, sh;
+    int dtype;
+};
+
+// (d, H, N, B) view with a {64, 1, 128, 1} box and 128-byte swizzle: one box = 128 rows of 128 B,
+// the layout both the tcgen05 smem descriptors and the epilogue assume.
+int make_tensor_map(CUtensorMap* out, const void* ptr, const Problem& p) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FA_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    const cuuint64_t dims[4] = {128, (cuuint64_t)p.H, (cuuint64_t)p.N, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.sh * 2, (cuuint64_t)p.sn * 2,
+                                   (cuuint64_t)p.sb * 2};
+    const cuuint32_t box[4] = {64, 1, 128, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = (p.dtype == FA_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FA_ERR_TENSORMAP,
+                    "cuTensorMapEncodeTiled failed (CUresult %d) for shape (%d,%d,%d,128) strides "
+                    "(%lld,%lld,%lld)",
+                    (int)r, p.B, p.N, p.H, (long long)p.sb, (long long)p.sn, (long long)p.sh);
+    return FA_OK;
+}
+
+int validate(const Problem& p, int d_head) {
+    if (p.dtype != FA_DTYPE_FP16 && p.dtype != FA_DTYPE_BF16)
+        return fail(FA_ERR_DTYPE, "Only fp16 and bf16 are supported");
+    if (d_head != fa::kHeadDim)
+        return fail(FA_ERR_DHEAD, "Kernel configuration was not found: d_head must be 128 (got %d)",
+                    d_head);
+    if (!p.q || !p.k || !p.v || !p.o) return fail(FA_ERR_ARG, "null tensor pointer");
+    if (p.B <= 0 || p.N <= 0 || p.H <= 0)
+        return fail(FA_ERR_ARG, "batch, seq_len and n_heads must be positive");
+    if (p.N % fa::kBlockN != 0)
+        return fail(FA_ERR_SEQLEN,
+                    "Only multiples of B_r are supported for seq_len Q currently (B_r = B_c = 128, "
+                    "seq_len = %d)",
+                    p.N);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.k) |
+                        reinterpret_cast<uintptr_t>(p.v) | reinterpret_cast<uintptr_t>(p.o);
+    if (a & 15) return fail(FA_ERR_ARG, "tensor pointers must be 16-byte aligned");
+    if (p.sb <= 0 || p.sn <= 0 || p.sh <= 0 || ((p.sb | p.sn | p.sh) & 7))
+        return fail(FA_ERR_ARG, "strides must be positive multiples of 8 elements (16 bytes)");
+    return FA_OK;
+}
+
+template <bool kDebug>
+int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
+    int dev = -1;
+    FA_CUDA(cudaGetDevice(&dev));
+    int rc = init_device(dev);
+    if (rc != FA_OK) return rc;
+
+    CUtensorMap tq, tk, tv, to;
+    if ((rc = make_tensor_map(&tq, p.q, p)) != FA_OK) return rc;
+    if ((rc = make_tensor_map(&tk, p.k, p)) != FA_OK) return rc;
+    if ((rc = make_tensor_map(&tv, p.v, p)) != FA_OK) return rc;
+    if ((rc = make_tensor_map(&to, p.o, p)) != FA_OK) return rc;
+
+    fa::FwdParams prm;
+    prm.batch = p.B;
+    prm.seq_len = p.N;
+    prm.n_heads = p.H;
+    prm.n_kv_blocks = p.N / fa::kBlockN;
+    prm.n_q_pairs = (p.N + fa::kQStages * fa::kBlockM - 1) / (fa::kQStages * fa::kBlockM);
+    prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
+
+    const long long n_ctas = 1LL * p.B * p.H * prm.n_q_pairs;
+    if (n_ctas > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld CTAs", n_ctas);
+    dim3 grid((unsigned)n_ctas), block(fa::kNumThreads);
+    if (p.dtype == FA_DTYPE_BF16)
+        fa::fa_fwd_kernel<true, kDebug>
+            <<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
+    else
+        fa::fa_fwd_kernel<false, kDebug>
+            <<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    FA_CUDA(cudaGetLastError());
+    return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer path
+// ---------------------------------------------------------------------------------------------
+struct HostWorkspace {
+    std::mutex mu;
+    size_t bytes = 0;  // per tensor
+    void* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_run;
+};
+HostWorkspace g_ws[kMaxDevices];
+
+void ws_release(HostWorkspace& w) {
+    for (auto& p : w.d) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    w.bytes = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fa_last_error_string(void) { return g_err; }
+
+int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_capability) {
+    cudaDeviceProp prop;
+    FA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (n_sms) *n_sms = prop.multiProcessorCount;
+    if (smem_optin_bytes) *smem_optin_bytes = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (compute_capability) *compute_capability = prop.major * 10 + prop.minor;
+    return FA_OK;
+}
+
+int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_cols) {
+    if (smem_bytes) *smem_bytes = fa::kSmemLaunchBytes;
+    if (threads) *threads = fa::kNumThreads;
+    if (rows_per_cta) *rows_per_cta = fa::kQStages * fa::kBlockM;
+    if (tmem_cols) *tmem_cols = fa::kTmemCols;
+    return FA_OK;
+}
+
+int fa_fwd(const void* q, const void* k, const void* v, void* o, int batch, int seq_len,
+           int n_heads, int d_head, int64_t stride_batch, int64_t stride_seq, int64_t stride_head,
+           int dtype, void* stream) {
+    g_err[0] = 0;
+    Problem p{q, k, v, o, batch, seq_len, n_heads, stride_batch, stride_seq, stride_head, dtype};
+    int rc = validate(p, d_head);
+    if (rc != FA_OK) return rc;
+    fa::FwdDebug dbg{};
+    return launch<false>(p, static_cast<cudaStream_t>(stream), dbg);
+}
+
+int fa_fwd_timed(const void* q, const void* k, const void* v, void* o, int batch, int seq_len,
+                 int n_heads, int d_head, int64_t stride_batch, int64_t stride_seq,
+                 int64_t stride_head, int dtype, void* stream, float* ms) {
+    g_err[0] = 0;
+    if (!ms) return fail(FA_ERR_ARG, "ms must not be null");
+    Problem p{q, k, v, o, batch, seq_len, n_heads, stride_batch, stride_seq, stride_head, dtype};
+    int rc = validate(p, d_head);
+    if (rc != FA_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t e0, e1;
+    FA_CUDA(cudaEventCreate(&e0));
+    FA_CUDA(cudaEventCreate(&e1));
+    fa::FwdDebug dbg{};
+    cudaEventRecord(e0, st);
+    rc = launch<false>(p, st, dbg);
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (rc == FA_OK && e != cudaSuccess)
+        rc = fail(FA_ERR_LAUNCH, "kernel execution failed: %s", cudaGetErrorString(e));
+    if (rc == FA_OK) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int fa_fwd_debug(const void* q, const void* k, const void* v, void* o, int batch, int seq_len,
+                 int n_heads, int d_head, int64_t stride_batch, int64_t stride_seq,
+                 int64_t stride_head, int dtype, float* dump, const uint32_t* knobs) {
+    g_err[0] = 0;
+    Problem p{q, k, v, o, batch, seq_len, n_heads, stride_batch, stride_seq, stride_head, dtype};
+    int rc = validate(p, d_head);
+    if (rc != FA_OK) return rc;
+    fa::FwdDebug dbg{};
+    dbg.dump = dump;
+    dbg.qk_lbo = knobs ? knobs[0] : 16;
+    dbg.qk_sbo = knobs ? knobs[1] : 1024;
+    dbg.v_lbo = knobs ? knobs[2] : fa::kHalfBytes;
+    dbg.v_sbo = knobs ? knobs[3] : 1024;
+    dbg.v_kstep = knobs ? knobs[4] : 2048;
+    dbg.p_swap = knobs ? knobs[5] : 0;
+    dbg.p_col_step = knobs ? knobs[6] : 8;
+    rc = launch<true>(p, nullptr, dbg);
+    if (rc != FA_OK) return rc;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess)
+        return fail(FA_ERR_LAUNCH, "debug kernel failed: %s", cudaGetErrorString(e));
+    return FA_OK;
+}
+
+int fa_host_workspace_free(int device) {
+    for (int d = 0; d < kMaxDevices; ++d) {
+        if (device >= 0 && d != device) continue;
+        HostWorkspace& w = g_ws[d];
+        std::lock_guard<std::mutex> lk(w.mu);
+        if (w.bytes == 0 && !w.s_in) continue;
+        int cur = -1;
+        cudaGetDevice(&cur);
+        cudaSetDevice(d);
+        ws_release(w);
+        for (auto e : w.ev_in) cudaEventDestroy(e);
+        for (auto e : w.ev_run) cudaEventDestroy(e);
+        w.ev_in.clear();
+        w.ev_run.clear();
+        if (w.s_in) cudaStreamDestroy(w.s_in);
+        if (w.s_run) cudaStreamDestroy(w.s_run);
+        if (w.s_out) cudaStreamDestroy(w.s_out);
+        w.s_in = w.s_run = w.s_out = nullptr;
+        if (cur >= 0) cudaSetDevice(cur);
+    }
+    return FA_OK;
+}
+
+int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void* o_host,
+                int batch, int seq_len, int n_heads, int d_head, int dtype, int device) {
+    g_err[0] = 0;
+    if (device < 0 || device >= kMaxDevices) return fail(FA_ERR_DEVICE, "bad device %d", device);
+    if (!q_host || !k_host || !v_host || !o_host) return fail(FA_ERR_ARG, "null host pointer");
+    if (d_head != fa::kHeadDim)
+        return fail(FA_ERR_DHEAD, "Kernel configuration was not found: d_head must be 128 (got %d)",
+                    d_head);
+    if (batch <= 0 || seq_len <= 0 || n_heads <= 0)
+        return fail(FA_ERR_ARG, "batch, seq_len and n_heads must be positive");
+    FA_CUDA(cudaSetDevice(device));
+    HostWorkspace& w = g_ws[device];
+    std::lock_guard<std::mutex> lk(w.mu);
+    const size_t per_batch = (size_t)seq_len * n_heads * d_head * 2;
+    const size_t total = per_batch * batch;
+    if (w.bytes < total) {
+        ws_release(w);
+        for (auto& p : w.d) FA_CUDA(cudaMalloc(&p, total));
+        w.bytes = total;
+    }
+    if (!w.s_in) {
+        FA_CUDA(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+        FA_CUDA(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
+        FA_CUDA(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    }
+    while ((int)w.ev_in.size() < batch) {
+        cudaEvent_t a, b;
+        FA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FA_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        w.ev_in.push_back(a);
+        w.ev_run.push_back(b);
+    }
+    const int64_t sh = d_head, sn = (int64_t)n_heads * d_head, sb = (int64_t)seq_len * sn;
+    // Software pipeline over the batch dimension: H2D(b+1) overlaps kernel(b) overlaps D2H(b-1).
+    for (int b = 0; b < batch; ++b) {
+        const size_t off = per_batch * b;
+        const void* src[3] = {q_host, k_host, v_host};
+        for (int t = 0; t < 3; ++t)
+            FA_CUDA(cudaMemcpyAsync((char*)w.d[t] + off, (const char*)src[t] + off, per_batch,
+                                    cudaMemcpyHostToDevice, w.s_in));
+        FA_CUDA(cudaEventRecord(w.ev_in[b], w.s_in));
+        FA_CUDA(cudaStreamWaitEvent(w.s_run, w.ev_in[b], 0));
+        int rc = fa_fwd((char*)w.d[0] + off, (char*)w.d[1] + off, (char*)w.d[2] + off,
+                        (char*)w.d[3] + off, 1, seq_len, n_heads, d_head, sb, sn, sh, dtype,
+                        w.s_run);
+        if (rc != FA_OK) return rc;
+        FA_CUDA(cudaEventRecord(w.ev_run[b], w.s_run));
+        FA_CUDA(cudaStreamWaitEvent(w.s_out, w.ev_run[b], 0));
+        FA_CUDA(cudaMemcpyAsync((char*)o_host + off, (char*)w.d[3] + off, per_batch,
+                                cudaMemcpyDeviceToHost, w.s_out));
+    }
+    FA_CUDA(cudaStreamSynchronize(w.s_out));
+    FA_CUDA(cudaStreamSynchronize(w.s_run));
+    return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// Fused attention forward for NVIDIA B200 (sm_100a):  O = softmax(Q K^T / sqrt(d)) V
+//
+// Replaces the reference's Ampere kernel `flash::flash_forward_kernel`
+// (/root/reference/src/include/forward_kernel.cuh:85-204) and its device primitives
+// (gemm.cuh / softmax.cuh / load_store.cuh).  Same arithmetic contract
+// (/root/reference/src/include/softmax.cuh:15-128, forward_kernel.cuh:150-152):
+//     c = log2(e)/sqrt(d);  m = running row max of raw S;  P = exp2(S*c - m*c) in fp32;
+//     l += rowsum(P) (un-rounded fp32);  O += rn16(P) V (fp32 accumulate);  out = rn16(O / l)
+// but a different machine mapping -- nothing of the mma.sync / ldmatrix / cp.async path is kept:
+//
+//   * one CTA = 2 Q tiles of 128 rows (256 query rows) of one (batch, head); 1 CTA per SM
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) stages Q once and K/V blocks through a ring of
+//     shared-memory slots guarded by full/empty mbarriers
+//   * one elected thread issues tcgen05.mma: S_s = Q_s K_j^T (operands from smem) and
+//     O_s += P_s V_j (P read from tensor memory, V from smem, MN-major); accumulators in TMEM:
+//       columns [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1
+//   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
+//     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit,
+//     lazy rescale of O (only when the row max grew by more than 2^8), final 1/l scaling and
+//     TMA store of O through swizzled shared memory.
+//   The two Q tiles ping-pong: while the tensor core runs PV_1(j-1) and S_1(j) the softmax
+//   warpgroup 0 works on S_0(j), and vice versa.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx_sm100.cuh"
+
+namespace fa {
+
+constexpr int kBlockM = 128;   // query rows per tile == TMEM lanes
+constexpr int kBlockN = 128;   // key/value rows per block
+constexpr int kHeadDim = 128;  // d_head (the only one the reference supports, README.md:9-15)
+constexpr int kQStages = 2;    // Q tiles per CTA
+constexpr int kKVStages = 4;   // K/V ring slots (each slot holds one K block or one V block)
+constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
+constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
+constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
+constexpr int kTmemCols = 512;
+
+constexpr int kSmemQ = 0;
+constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;
+constexpr int kSmemBar = kSmemKV + kKVStages * kTileBytes;
+constexpr int kNumBarriers = 2 + 2 * kKVStages + 6;
+constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
+constexpr int kSmemTotal = kSmemTmemPtr + 16;
+constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack for manual 1024 B alignment
+
+// Lazy rescale threshold in log2 units: O and l are only rescaled when the running max grows by
+// more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in fp32,
+// representable in bf16/fp16).  The final O/l is unaffected.
+constexpr float kRescaleThreshold = 8.0f;
+
+// Bring-up knobs (only read by the kDebug instantiation; see tools/gpu_bringup.py).
+struct FwdDebug {
+    float* dump;         // S(j=0) [2][128][128], O_raw [2][128][128], l [2][128], m [2][128] of CTA 0
+    uint32_t qk_lbo;     // descriptor byte offsets for the K-major Q/K tiles
+    uint32_t qk_sbo;
+    uint32_t v_lbo;      // descriptor byte offsets for the MN-major V tile
+    uint32_t v_sbo;
+    uint32_t v_kstep;    // bytes between consecutive 16-row k-steps of V
+    uint32_t p_swap;     // 1: swap the two 16-bit halves when packing P
+    uint32_t p_col_step; // TMEM columns between consecutive k-steps of P
+};
+
+struct FwdParams {
+    int batch;
+    int seq_len;
+    int n_heads;
+    int n_kv_blocks;   // seq_len / 128
+    int n_q_pairs;     // ceil(seq_len / 256): CTAs per (batch, head)
+    float scale_log2;  // log2(e) / sqrt(d_head)
+};
+
+template <bool kBF16, bool kDebug>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+              const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+              const FwdParams prm, const FwdDebug dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int wg = warp >> 2;
+
+    // barrier addresses
+    const uint32_t bar0 = smem_base + kSmemBar;
+    auto q_full = [&](int s) { return bar0 + 8u * s; };
+    auto kv_full = [&](int i) { return bar0 + 8u * (2 + i); };
+    auto kv_empty = [&](int i) { return bar0 + 8u * (2 + kKVStages + i); };
+    auto s_full = [&](int s) { return bar0 + 8u * (2 + 2 * kKVStages + s); };
+    auto p_full = [&](int s) { return bar0 + 8u * (4 + 2 * kKVStages + s); };
+    auto o_full = [&](int s) { return bar0 + 8u * (6 + 2 * kKVStages + s); };
+    const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
+
+    // tile coordinates: q-pair fastest so co-resident CTAs share K/V of one (b, h) in L2
+    const int tile = blockIdx.x;
+    const int qpair = tile % prm.n_q_pairs;
+    const int bh = tile / prm.n_q_pairs;
+    const int head = bh % prm.n_heads;
+    const int batch = bh / prm.n_heads;
+    const int n_blocks = prm.n_kv_blocks;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < kQStages; ++s) {
+                mbar_init(q_full(s), 1);
+                mbar_init(s_full(s), 1);
+                mbar_init(p_full(s), 4);  // one elected arrive per softmax warp
+                mbar_init(o_full(s), 1);
+            }
+            for (int i = 0; i < kKVStages; ++i) {
+                mbar_init(kv_full(i), 1);
+                mbar_init(kv_empty(i), 1);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, kTmemCols);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        tma_prefetch_desc(&tm_o);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr);
+
+    if (wg == 2) {
+        setmaxnreg_dec<96>();
+        if (warp == 9) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                const int q_row0 = qpair * (kQStages * kBlockM);
+                auto load_tile = [&](const CUtensorMap* map, uint32_t dst, uint32_t bar, int row0) {
+                    mbar_arrive_expect_tx(bar, kTileBytes);
+                    tma_load_4d(dst, map, bar, 0, head, row0, batch);
+                    tma_load_4d(dst + kHalfBytes, map, bar, 64, head, row0, batch);
+                };
+                int item = 0;  // ring item counter: K0, V0, K1, V1, ...
+                auto load_kv = [&](const CUtensorMap* map, int blk) {
+                    const int slot = item % kKVStages;
+                    const uint32_t use = item / kKVStages;
+                    mbar_wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
+                    load_tile(map, smem_base + kSmemKV + slot * kTileBytes, kv_full(slot),
+                              blk * kBlockN);
+                    ++item;
+                };
+                load_tile(&tm_q, smem_base + kSmemQ, q_full(0), q_row0);
+                load_kv(&tm_k, 0);
+                load_tile(&tm_q, smem_base + kSmemQ + kTileBytes, q_full(1), q_row0 + kBlockM);
+                load_kv(&tm_v, 0);
+                for (int j = 1; j < n_blocks; ++j) {
+                    load_kv(&tm_k, j);
+                    load_kv(&tm_v, j);
+                }
+            }
+        } else if (warp == 8) {
+            // ================================ MMA issuer ==================================
+            if (lane == 0) {
+                constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, kBlockM, kBlockN, false);
+                constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kBlockM, kHeadDim, true);
+                // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
+                // V tiles: MN-major; next 64-wide d chunk 16 KiB away (LBO), next 8 kv rows 1 KiB (SBO).
+                auto issue_qk = [&](int s, int slot) {
+                    const uint32_t lbo = kDebug ? dbg.qk_lbo : 16u;
+                    const uint32_t sbo = kDebug ? dbg.qk_sbo : 1024u;
+                    const uint64_t a0 =
+                        umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, lbo, sbo);
+                    const uint64_t b0 =
+                        umma_smem_desc_sw128(smem_base + kSmemKV + slot * kTileBytes, lbo, sbo);
+#pragma unroll
+                    for (int k = 0; k < kHeadDim / 16; ++k) {
+                        const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
+                        umma_ss(tmem_base + s * kBlockN, a0 + off, b0 + off, idesc_qk, k > 0);
+                    }
+                };
+                auto issue_pv = [&](int s, int slot, bool accumulate) {
+                    const uint32_t lbo = kDebug ? dbg.v_lbo : (uint32_t)kHalfBytes;
+                    const uint32_t sbo = kDebug ? dbg.v_sbo : 1024u;
+                    const uint32_t kstep = kDebug ? dbg.v_kstep : 2048u;
+                    const uint32_t pstep = kDebug ? dbg.p_col_step : 8u;
+                    const uint64_t b0 =
+                        umma_smem_desc_sw128(smem_base + kSmemKV + slot * kTileBytes, lbo, sbo);
+#pragma unroll
+                    for (int k = 0; k < kBlockN / 16; ++k) {
+                        umma_ts(tmem_base + 2 * kBlockN + s * kHeadDim,
+                                tmem_base + s * kBlockN + k * pstep, b0 + ((k * kstep) >> 4),
+                                idesc_pv, (accumulate || k > 0) ? 1u : 0u);
+                    }
+                };
+                int item = 0;
+                auto slot_of = [&](int it) { return it % kKVStages; };
+                auto parity_of = [&](int it) { return (uint32_t)((it / kKVStages) & 1); };
+
+                // prologue: S_s = Q_s K_0^T
+                mbar_wait(kv_full(slot_of(0)), parity_of(0), 200);
+                for (int s = 0; s < kQStages; ++s) {
+                    mbar_wait(q_full(s), 0, 210 + s);
+                    tc_fence_after();
+                    issue_qk(s, slot_of(0));
+                    umma_commit(s_full(s));
+                }
+                umma_commit(kv_empty(slot_of(0)));
+                item = 1;
+                for (int j = 0; j < n_blocks; ++j) {
+                    const int it_v = item;      // V_j
+                    const int it_k = item + 1;  // K_{j+1}
+                    const bool has_next = (j + 1 < n_blocks);
+                    mbar_wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
+                    for (int s = 0; s < kQStages; ++s) {
+                        mbar_wait(p_full(s), j & 1, 230 + s);  // P_s(j) stored, O_s rescaled
+                        tc_fence_after();
+                        issue_pv(s, slot_of(it_v), j > 0);
+                        if (has_next) {
+                            if (s == 0) {
+                                mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
+                                tc_fence_after();
+                            }
+                            issue_qk(s, slot_of(it_k));
+                            umma_commit(s_full(s));
+                        } else {
+                            umma_commit(o_full(s));
+                        }
+                    }
+                    umma_commit(kv_empty(slot_of(it_v)));
+                    if (has_next) umma_commit(kv_empty(slot_of(it_k)));
+                    item += 2;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ==================================== softmax =====================================
+        setmaxnreg_inc<208>();
+        const int s = wg;                    // Q tile handled by this warpgroup
+        const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
+        const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_sel + s * kBlockN;
+        const uint32_t t_p = t_s;
+        const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim;
+        const float c = prm.scale_log2;
+
+        float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
+        float l_run = 0.f;        // running row sum of exp2
+
+        for (int j = 0; j < n_blocks; ++j) {
+            mbar_wait(s_full(s), j & 1, 300 + s);
+            tc_fence_after();
+            uint32_t sr[4][32];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+            tmem_wait_ld();
+
+            if constexpr (kDebug) {
+                if (dbg.dump != nullptr && blockIdx.x == 0 && j == 0) {
+                    for (int q = 0; q < 4; ++q)
+                        for (int i = 0; i < 32; ++i)
+                            dbg.dump[(s * 128 + row) * 128 + q * 32 + i] =
+                                __uint_as_float(sr[q][i]);
+                }
+            }
+            float mx = m_run;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[q][i]));
+            }
+            float alpha = 1.f;
+            if (j == 0) {
+                m_run = mx;
+            } else {
+                const float delta = (mx - m_run) * c;  // >= 0
+                const bool need = delta > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    if (need) {
+                        alpha = ex2_approx(-delta);
+                        m_run = mx;
+                    }
+                    // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[32];
+                        tmem_ld_32x32b_x32(t_o + q * 32, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32b_x32(t_o + q * 32, o);
+                    }
+                }
+            }
+            const float neg_mc = -m_run * c;
+            float sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[q][i]), c, neg_mc));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[q][i + 1]), c, neg_mc));
+                    sum += p0 + p1;
+                    pk[i >> 1] = (kDebug && dbg.p_swap) ? pack_16x2<kBF16>(p1, p0)
+                                                        : pack_16x2<kBF16>(p0, p1);
+                }
+                tmem_st_32x32b_x16(t_p + q * 16, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(s));
+            l_run = l_run * alpha + sum;
+        }
+
+        // --------------------------------- epilogue --------------------------------------
+        mbar_wait(o_full(s), 0, 310 + s);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        // O tile is staged in the (now dead) Q_s region using the TMA 128B swizzle:
+        // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row.
+        uint8_t* o_stage = smem_gen + kSmemQ + s * kTileBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + q * 32, o);
+            tmem_wait_ld();
+            if constexpr (kDebug) {
+                if (dbg.dump != nullptr && blockIdx.x == 0) {
+                    for (int i = 0; i < 32; ++i)
+                        dbg.dump[2 * 128 * 128 + (s * 128 + row) * 128 + q * 32 + i] =
+                            __uint_as_float(o[i]);
+                    dbg.dump[4 * 128 * 128 + s * 128 + row] = l_run;
+                    dbg.dump[4 * 128 * 128 + 256 + s * 128 + row] = m_run;
+                }
+            }
+            uint8_t* half_base = o_stage + (q >> 1) * kHalfBytes + row * 128;
+#pragma unroll
+            for (int cidx = 0; cidx < 4; ++cidx) {
+                uint4 v;
+                v.x = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 0]) * inv_l,
+                                       __uint_as_float(o[cidx * 8 + 1]) * inv_l);
+                v.y = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 2]) * inv_l,
+                                       __uint_as_float(o[cidx * 8 + 3]) * inv_l);
+                v.z = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 4]) * inv_l,
+                                       __uint_as_float(o[cidx * 8 + 5]) * inv_l);
+                v.w = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 6]) * inv_l,
+                                       __uint_as_float(o[cidx * 8 + 7]) * inv_l);
+                const int chunk = ((q & 1) * 4 + cidx) ^ (row & 7);
+                *reinterpret_cast<uint4*>(half_base + chunk * 16) = v;
+            }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + s, 128);
+        if (row == 0) {
+            const int q_row = qpair * (kQStages * kBlockM) + s * kBlockM;
+            const uint32_t src = smem_base + kSmemQ + s * kTileBytes;
+            tma_store_4d(&tm_o, src, 0, head, q_row, batch);
+            tma_store_4d(&tm_o, src + kHalfBytes, 64, head, q_row, batch);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+        }
+    }
+
+    // ------------------------------------ teardown ---------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace fa
