@@ -29,7 +29,7 @@ SYMBOLS = {
     "fa_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
     "fa_launch_count": (_L, []),
-    "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32)]),
+    "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32), _P]),
 }
 
 _lib = None

@@ -294,7 +294,8 @@ int fa_fwd_timed(const void* q, const void* k, const void* v, void* o, int batch
 
 int fa_fwd_debug(const void* q, const void* k, const void* v, void* o, int batch, int seq_len,
                  int n_heads, int d_head, int64_t stride_batch, int64_t stride_seq,
-                 int64_t stride_head, int dtype, float* dump, const uint32_t* knobs) {
+                 int64_t stride_head, int dtype, float* dump, const uint32_t* knobs,
+                 uint32_t* diag) {
     g_err[0] = 0;
     Problem p{q, k, v, o, batch, seq_len, n_heads, stride_batch, stride_seq, stride_head, dtype};
     int rc = validate(p, d_head);
@@ -308,6 +309,8 @@ int fa_fwd_debug(const void* q, const void* k, const void* v, void* o, int batch
     dbg.v_kstep = knobs ? knobs[4] : 2048;
     dbg.p_swap = knobs ? knobs[5] : 0;
     dbg.p_col_step = knobs ? knobs[6] : 8;
+    dbg.level = knobs ? knobs[7] : 4;
+    dbg.diag = diag;
     rc = launch<true>(p, nullptr, dbg);
     if (rc != FA_OK) return rc;
     cudaError_t e = cudaDeviceSynchronize();

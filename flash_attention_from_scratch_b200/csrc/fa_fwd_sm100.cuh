@@ -63,6 +63,9 @@ struct FwdDebug {
     uint32_t v_kstep;    // bytes between consecutive 16-row k-steps of V
     uint32_t p_swap;     // 1: swap the two 16-bit halves when packing P
     uint32_t p_col_step; // TMEM columns between consecutive k-steps of P
+    uint32_t level;      // 1: setup/teardown only, 2: + TMA Q0,K0 (raw smem dump), 3: + S = QK^T
+                         // (S dump), >= 4: everything
+    uint32_t* diag;      // host-mapped diagnostics (hang-guard builds)
 };
 
 struct FwdParams {
@@ -105,6 +108,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const int batch = bh / prm.n_heads;
     const int n_blocks = prm.n_kv_blocks;
 
+    const uint32_t level = kDebug ? dbg.level : 4u;
+#if FA_HANG_GUARD
+    if constexpr (kDebug) {
+        if (threadIdx.x == 0) g_fa_diag = dbg.diag;
+    }
+#endif
     if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < kQStages; ++s) {
@@ -134,7 +143,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr);
 
     if (wg == 2) {
-        setmaxnreg_dec<96>();
+        setmaxnreg_dec<104>();
         if (warp == 9) {
             // ================================ TMA producer ================================
             if (lane == 0) {
@@ -153,13 +162,18 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                               blk * kBlockN);
                     ++item;
                 };
-                load_tile(&tm_q, smem_base + kSmemQ, q_full(0), q_row0);
-                load_kv(&tm_k, 0);
-                load_tile(&tm_q, smem_base + kSmemQ + kTileBytes, q_full(1), q_row0 + kBlockM);
-                load_kv(&tm_v, 0);
-                for (int j = 1; j < n_blocks; ++j) {
-                    load_kv(&tm_k, j);
-                    load_kv(&tm_v, j);
+                if (level >= 2) {
+                    load_tile(&tm_q, smem_base + kSmemQ, q_full(0), q_row0);
+                    load_kv(&tm_k, 0);
+                }
+                if (level >= 3)
+                    load_tile(&tm_q, smem_base + kSmemQ + kTileBytes, q_full(1), q_row0 + kBlockM);
+                if (level >= 4) {
+                    load_kv(&tm_v, 0);
+                    for (int j = 1; j < n_blocks; ++j) {
+                        load_kv(&tm_k, j);
+                        load_kv(&tm_v, j);
+                    }
                 }
             }
         } else if (warp == 8) {
@@ -200,6 +214,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 auto slot_of = [&](int it) { return it % kKVStages; };
                 auto parity_of = [&](int it) { return (uint32_t)((it / kKVStages) & 1); };
 
+                if constexpr (kDebug) {
+                    if (level == 2) {  // raw smem images of Q0 and K0 as TMA wrote them
+                        mbar_wait(kv_full(0), 0, 200);
+                        mbar_wait(q_full(0), 0, 210);
+                        if (dbg.dump != nullptr && blockIdx.x == 0) {
+                            const uint32_t* qs = reinterpret_cast<const uint32_t*>(smem_gen + kSmemQ);
+                            const uint32_t* ks = reinterpret_cast<const uint32_t*>(smem_gen + kSmemKV);
+                            uint32_t* out = reinterpret_cast<uint32_t*>(dbg.dump);
+                            for (int i = 0; i < kTileBytes / 4; ++i) out[i] = qs[i];
+                            for (int i = 0; i < kTileBytes / 4; ++i) out[kTileBytes / 4 + i] = ks[i];
+                        }
+                    }
+                }
+                if (level >= 3) {
                 // prologue: S_s = Q_s K_0^T
                 mbar_wait(kv_full(slot_of(0)), parity_of(0), 200);
                 for (int s = 0; s < kQStages; ++s) {
@@ -209,8 +237,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     umma_commit(s_full(s));
                 }
                 umma_commit(kv_empty(slot_of(0)));
+                }
                 item = 1;
-                for (int j = 0; j < n_blocks; ++j) {
+                for (int j = 0; level >= 4 && j < n_blocks; ++j) {
                     const int it_v = item;      // V_j
                     const int it_k = item + 1;  // K_{j+1}
                     const bool has_next = (j + 1 < n_blocks);
@@ -239,7 +268,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
     } else {
         // ==================================== softmax =====================================
-        setmaxnreg_inc<208>();
+        setmaxnreg_inc<200>();
         const int s = wg;                    // Q tile handled by this warpgroup
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -251,7 +280,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
         float l_run = 0.f;        // running row sum of exp2
 
-        for (int j = 0; j < n_blocks; ++j) {
+        const int n_iter = (level >= 4) ? n_blocks : (level == 3 ? 1 : 0);
+        for (int j = 0; j < n_iter; ++j) {
             mbar_wait(s_full(s), j & 1, 300 + s);
             tc_fence_after();
             uint32_t sr[4][32];
@@ -266,6 +296,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                             dbg.dump[(s * 128 + row) * 128 + q * 32 + i] =
                                 __uint_as_float(sr[q][i]);
                 }
+            }
+            if constexpr (kDebug) {
+                if (level == 3) break;
             }
             float mx = m_run;
 #pragma unroll
@@ -320,6 +353,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
 
         // --------------------------------- epilogue --------------------------------------
+        if (level >= 4) {
         mbar_wait(o_full(s), 0, 310 + s);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
@@ -365,6 +399,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             tma_store_4d(&tm_o, src + kHalfBytes, 64, head, q_row, batch);
             tma_store_commit();
             tma_store_wait_read<0>();
+        }
         }
     }
 

@@ -58,11 +58,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Blocks until the phase with the given parity has completed.  With FA_HANG_GUARD the spin is
 // bounded and traps with a diagnostic instead of hanging the GPU (bring-up builds only).
+#if FA_HANG_GUARD
+// Host-mapped diagnostics ring (bring-up builds): [0] = record count, then 4 words per record.
+__device__ uint32_t* g_fa_diag = nullptr;
+__device__ __forceinline__ void diag_record(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t* p = g_fa_diag;
+    if (p == nullptr) return;
+    const uint32_t i = atomicAdd(p, 1u);
+    if (i < 60) {
+        p[4 + 4 * i + 0] = a;
+        p[4 + 4 * i + 1] = b;
+        p[4 + 4 * i + 2] = c;
+        p[4 + 4 * i + 3] = d;
+    }
+    __threadfence_system();
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
 #if FA_HANG_GUARD
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         if (mbar_try_wait(bar, parity)) return;
     }
+    diag_record(0xDEAD0000u | (uint32_t)tag, parity, threadIdx.x, blockIdx.x);
     printf("[fa] mbarrier timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
            (int)threadIdx.x, tag, parity);
     __trap();

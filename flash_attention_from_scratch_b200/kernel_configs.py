@@ -1,0 +1,158 @@
+"""Kernel-config surface compatible with the reference's `flash_helpers.kernel_configs`
+(/root/reference/py/flash_helpers/kernel_configs.py:9-175, 389-485).
+
+The reference uses a 13-field frozen dataclass as the key into a registry of 85 Ampere template
+instantiations.  The B200 library has ONE kernel per dtype, so here the dataclass is a
+description/compatibility object: the operator only reads `dtype` and `d_head`
+(see op.py); the mma.sync tiling knobs are carried so that reference scripts that print, sort or
+parse configs keep working, but they select nothing.
+"""
+from __future__ import annotations
+
+import os
+import re
+from dataclasses import dataclass
+from enum import IntEnum
+
+ELEM_SIZE = 2  # bytes per element (fp16 / bf16)
+
+
+class DType(IntEnum):
+    """Values are torch ScalarType ints, as in the reference (kernel_configs.py:9-14); they are
+    also the dtype codes of the C ABI (include/fa_sm100.h)."""
+
+    FP16 = 5
+    BF16 = 15
+
+    def to_torch_dtype(self):
+        import torch
+
+        return {DType.FP16: torch.float16, DType.BF16: torch.bfloat16}[self]
+
+    def to_cpp_str(self) -> str:
+        return {DType.FP16: "FA_DTYPE_FP16", DType.BF16: "FA_DTYPE_BF16"}[self]
+
+    @classmethod
+    def from_string(cls, text: str) -> "DType":
+        text = text.strip()
+        if text.lstrip("-").isdigit():
+            return cls(int(text))
+        try:
+            return cls[text.upper()]
+        except KeyError:
+            raise ValueError(
+                f"Invalid dtype string '{text}'. Valid options: "
+                + ", ".join(f"{m.name} ({m.value})" for m in cls)
+            ) from None
+
+    @classmethod
+    def from_torch_dtype(cls, dt) -> "DType":
+        import torch
+
+        return {torch.float16: cls.FP16, torch.bfloat16: cls.BF16}[dt]
+
+
+def calc_self_attn_flop(n_samples: int, n_heads: int, seq_len: int, d_head: int) -> int:
+    """The reference's README/benchmark FLOP model, B*H*(4 N^2 d + 6 N^2)
+    (kernel_configs.py:102-103).  Used only for README-comparable columns."""
+    return n_samples * n_heads * (4 * seq_len**2 * d_head + 6 * seq_len**2)
+
+
+def calc_matmul_flop(n_samples: int, n_heads: int, seq_len: int, d_head: int) -> int:
+    """Algorithmic work used for the roofline: 4*B*H*N^2*d (QK^T + PV, 2 flop per MAC)."""
+    return 4 * n_samples * n_heads * seq_len**2 * d_head
+
+
+def algorithmic_bytes(n_samples: int, n_heads: int, seq_len: int, d_head: int) -> int:
+    """Q, K, V read once and O written once."""
+    return 4 * n_samples * seq_len * n_heads * d_head * ELEM_SIZE
+
+
+@dataclass(frozen=True, order=True)
+class FlashForwardKernelConfig:
+    """Field-compatible with kernel_configs.py:106-120 of the reference."""
+
+    dtype: DType
+    d_head: int = 128
+    B_r: int = 128
+    B_c: int = 128
+    n_warps: int = 12
+    async_copy: bool = True
+    eager_load_blocks: bool = True
+    swizzled: bool = True
+    Q_mma_load_K_tiles: int = 0
+    K_mma_load_K_tiles: int = 0
+    V_mma_load_K_tiles: int = 0
+    mma_double_buffer_loads: bool = False
+    optimized_softmax: bool = True
+
+    def __str__(self) -> str:
+        return self.short_form()
+
+    def short_form(self, include_d_head: bool = True, include_tup: bool = True) -> str:
+        feats = [name for flag, name in ((self.async_copy, "async"), (self.eager_load_blocks, "eager"),
+                                         (self.swizzled, "swizzled")) if flag]
+        feats.append(f"load_{self.Q_mma_load_K_tiles}_{self.K_mma_load_K_tiles}_"
+                     f"{self.V_mma_load_K_tiles}_tiles")
+        if self.mma_double_buffer_loads:
+            feats.append("buffer")
+        if self.optimized_softmax:
+            feats.append("opt_softmax")
+        head = ""
+        if include_tup:
+            d = f"{self.d_head}, " if include_d_head else ""
+            head = f"({self.dtype.name}, {d}{self.B_r}, {self.B_c}, {self.n_warps}): "
+        return head + "+".join(feats)
+
+    def kernel_name(self) -> str:
+        return "fa_fwd_kernel"
+
+    def attn_flop(self, n_samples: int, n_heads: int, seq_len: int) -> int:
+        return calc_self_attn_flop(n_samples, n_heads, seq_len, self.d_head)
+
+    def total_flop(self, n_samples: int, n_heads: int, seq_len: int) -> int:
+        return calc_matmul_flop(n_samples, n_heads, seq_len, self.d_head)
+
+
+_SHORT_RE = re.compile(r"\(\s*(\w+)\s*,\s*(\d+)\s*,\s*(\d+)\s*,\s*(\d+)\s*,\s*(\d+)\s*\)\s*:\s*(\S*)")
+
+
+def parse_kernel_name_into_config(text: str) -> FlashForwardKernelConfig:
+    """Parses the short form `(BF16, 128, 128, 128, 12): async+...+load_a_b_c_tiles+...`
+    (the format of the reference's tables, kernel_configs.py:253-331)."""
+    m = _SHORT_RE.search(text)
+    if not m:
+        raise ValueError(f"Invalid kernel name: {text}")
+    dtype, d_head, b_r, b_c, n_warps, feats = m.groups()
+    feats = feats.split("+")
+    load = next((f for f in feats if f.startswith("load_")), "load_0_0_0_tiles")
+    qt, kt, vt = (int(x) for x in load[len("load_"):-len("_tiles")].split("_"))
+    return FlashForwardKernelConfig(
+        dtype=DType.from_string(dtype), d_head=int(d_head), B_r=int(b_r), B_c=int(b_c),
+        n_warps=int(n_warps), async_copy="async" in feats, eager_load_blocks="eager" in feats,
+        swizzled="swizzled" in feats, Q_mma_load_K_tiles=qt, K_mma_load_K_tiles=kt,
+        V_mma_load_K_tiles=vt, mma_double_buffer_loads="buffer" in feats,
+        optimized_softmax="opt_softmax" in feats)
+
+
+def get_kernels_to_build():
+    """One kernel per dtype (the reference returns its 80-config autotune grid here,
+    kernel_configs.py:457-462; Ampere tile knobs have no meaning for tcgen05)."""
+    return sorted(FlashForwardKernelConfig(dtype=dt) for dt in DType)
+
+
+def get_autotuning_kernel_configs(dtypes=(DType.BF16, DType.FP16)):
+    return [FlashForwardKernelConfig(dtype=dt) for dt in dtypes]
+
+
+def get_kernel_configs(kernels_key: str = ""):
+    """Same `KERNELS` env UX as the reference (kernel_configs.py:465-485); every key maps onto the
+    per-dtype kernels; "B_r,B_c" keeps only matching tile sizes (i.e. "128,128")."""
+    if kernels_key == "":
+        kernels_key = os.environ.get("KERNELS", "all")
+    if kernels_key.startswith("prog") or kernels_key in ("all", "tune"):
+        return get_kernels_to_build()
+    if "," in kernels_key:
+        b_r, b_c = map(int, kernels_key.split(","))
+        return [c for c in get_kernels_to_build() if c.B_r == b_r and c.B_c == b_c]
+    raise ValueError(f"Invalid kernels env key: {kernels_key}")

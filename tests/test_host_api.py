@@ -1,0 +1,107 @@
+"""CPU tests of the host side: the C-ABI library builds for sm_100a, loads without a GPU, exports
+every symbol include/fa_sm100.h declares; the operator's argument checks mirror the reference
+launcher's error behaviour (/root/reference/src/flash_attention.cu:38-98).  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fa_sm100.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from flash_attention_from_scratch_b200 import _lib
+
+    declared = _declared_symbols()
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == declared
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(lib):
+    from flash_attention_from_scratch_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.lib_path())], capture_output=True,
+                          text=True).stdout
+    assert "EF_CUDA_SM100" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass  # no legacy mma.sync path
+
+
+def test_kernel_info(lib):
+    from flash_attention_from_scratch_b200 import _lib
+
+    info = _lib.kernel_info()
+    assert info["rows_per_cta"] == 256 and info["tmem_cols"] == 512
+    assert info["smem_bytes"] <= 227 * 1024
+    assert _lib.launch_count() == 0 or torch.cuda.is_available()
+
+
+def test_c_abi_argument_validation_without_gpu(lib):
+    from flash_attention_from_scratch_b200 import _lib
+
+    buf = C.create_string_buffer(4096 + 64)
+    p = (C.addressof(buf) + 63) & ~63
+    args = lambda **kw: (p, p, p, p, kw.get("B", 1), kw.get("N", 128), kw.get("H", 1),  # noqa: E731
+                         kw.get("D", 128), kw.get("sb", 128 * 128), kw.get("sn", 128), kw.get("sh", 128),
+                         kw.get("dtype", 15), None)
+    assert lib.fa_fwd(*args(dtype=6)) == 1 and "Only fp16 and bf16" in _lib.last_error()
+    assert lib.fa_fwd(*args(D=64)) == 2 and "Kernel configuration was not found" in _lib.last_error()
+    assert lib.fa_fwd(*args(N=192)) == 3 and "multiples of B_r" in _lib.last_error()
+    assert lib.fa_fwd(*args(B=0)) == 4
+    assert lib.fa_fwd(*args(sn=100)) == 4 and "strides" in _lib.last_error()
+    a = list(args())
+    a[0] = None
+    assert lib.fa_fwd(*a) == 4
+    if not torch.cuda.is_available():
+        # valid arguments but no device: must fail loudly, never fall back
+        rc = lib.fa_fwd(*args())
+        assert rc in (5, 7), rc
+        assert _lib.last_error() != ""
+
+
+def test_operator_checks_mirror_reference_messages():
+    import flash_attention
+    from flash_helpers.kernel_configs import DType, FlashForwardKernelConfig
+
+    cfg = FlashForwardKernelConfig(dtype=DType.BF16)
+    q = torch.zeros(1, 128, 2, 128, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        flash_attention.forward(cfg, q, q, q)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback_exists():
+    import flash_attention_from_scratch_b200 as pkg
+
+    src = open(os.path.join(os.path.dirname(pkg.__file__), "op.py")).read()
+    assert "oracle" not in src and "scaled_dot_product_attention" not in src
+
+
+def test_kernel_configs_surface():
+    from flash_helpers.kernel_configs import (DType, FlashForwardKernelConfig, calc_self_attn_flop,
+                                              get_kernel_configs, get_kernels_to_build,
+                                              parse_kernel_name_into_config)
+
+    assert DType.FP16 == 5 and DType.BF16 == 15
+    assert DType.BF16.to_torch_dtype() == torch.bfloat16
+    assert DType.from_string("bf16") == DType.BF16 and DType.from_string("5") == DType.FP16
+    cfgs = get_kernels_to_build()
+    assert {c.dtype for c in cfgs} == {DType.FP16, DType.BF16}
+    for c in cfgs:
+        assert parse_kernel_name_into_config(str(c)) == c
+    assert get_kernel_configs("128,128") == cfgs and get_kernel_configs("64,64") == []
+    # FLOP model of the reference README (kernel_configs.py:102-103)
+    assert calc_self_attn_flop(4, 32, 4096, 128) == 4 * 32 * (4 * 4096**2 * 128 + 6 * 4096**2)
+    assert FlashForwardKernelConfig(dtype=DType.BF16).total_flop(4, 32, 4096) == 4 * 4 * 32 * 4096**2 * 128

@@ -2,8 +2,10 @@
 """GPU bring-up driver: localises descriptor / layout mistakes in one gpurun round trip.
 
 Each experiment runs in its own subprocess under a timeout (a trapped or hung kernel kills only
-that subprocess).  The debug instantiation of the kernel dumps S(j=0), un-normalised O, l and m of
-CTA 0 so QK^T, the softmax and PV can be checked separately against torch on the same inputs.
+that subprocess).  The debug instantiation of the kernel is run at increasing `level`s
+(1 setup only, 2 TMA only, 3 + QK^T, 4 everything) and dumps raw smem tiles / S(j=0) /
+un-normalised O / l / m of CTA 0 into HOST-MAPPED memory, so the data survives a trapped kernel
+and QK^T, the softmax and PV can be checked separately against torch on the same inputs.
 
   python tools/gpu_bringup.py            # run the whole ladder
   python tools/gpu_bringup.py --one ...  # (internal) single experiment
@@ -20,6 +22,24 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+DUMP_WORDS = 4 * 128 * 128 + 512
+
+
+def swizzled_image(t):
+    """Expected smem image (as int32 words) of a (128, 128) 16-bit tile loaded as two
+    {64 cols x 128 rows} TMA boxes with SWIZZLE_128B: 16-byte chunk c of row r sits at chunk
+    c ^ (r & 7) of that row inside its 16 KiB half."""
+    import torch
+    halves = []
+    for h in range(2):
+        x = t[:, 64 * h: 64 * h + 64].contiguous().view(128, 8, 8)  # rows, chunks, 8 elems
+        out = torch.empty_like(x)
+        for r in range(128):
+            for c in range(8):
+                out[r, c ^ (r & 7)] = x[r, c]
+        halves.append(out.reshape(-1))
+    return torch.cat(halves).view(torch.int32)
+
 
 def run_one(args):
     import torch
@@ -34,71 +54,91 @@ def run_one(args):
     k = torch.randn_like(q)
     v = torch.randn_like(q)
     o = torch.zeros_like(q)
-    dump = torch.zeros(4 * 128 * 128 + 512, device="cuda", dtype=torch.float32)
-    knobs = (C.c_uint32 * 7)(*args.knobs)
+    dump = torch.zeros(DUMP_WORDS, dtype=torch.float32).pin_memory()
+    diag = torch.zeros(256, dtype=torch.int32).pin_memory()
+    knobs = (C.c_uint32 * 8)(*args.knobs)
+    level = args.knobs[7]
     sb, sn, sh, _ = q.stride()
     code = 15 if dt == torch.bfloat16 else 5
-    rc = lib.fa_fwd_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, N, H, D, sb,
-                          sn, sh, code, dump.data_ptr(), knobs)
-    if rc != 0:
-        print(json.dumps({"rc": rc, "err": _lib.last_error()}))
-        return
-    torch.cuda.synchronize()
-    res = {"rc": 0}
-    # reference for CTA 0 = (b=0, h=0, rows 0..255)
+    # references computed BEFORE the risky launch (the context may die)
     rows = min(256, N)
-    qf = q[0, :rows, 0].float()
-    kf = k[0, :, 0].float()
-    vf = v[0, :, 0].float()
-    S0 = qf @ kf[:128].T  # first KV block, raw scores
-    S_dump = dump[: 2 * 128 * 128].view(256, 128)[:rows]
-    res["S_maxerr"] = (S_dump - S0).abs().max().item()
-    res["S_ref_absmax"] = S0.abs().max().item()
-    # full attention reference
-    scale = 1.0 / (D ** 0.5)
-    Sfull = (qf @ kf.T) * scale
-    P = torch.softmax(Sfull, dim=-1)
-    Oref = P @ vf
-    o_cta = o[0, :rows, 0].float()
-    res["O_maxerr"] = (o_cta - Oref).abs().max().item()
-    res["O_ref_absmax"] = Oref.abs().max().item()
-    l_d = dump[4 * 128 * 128: 4 * 128 * 128 + 256][:rows]
-    m_d = dump[4 * 128 * 128 + 256: 4 * 128 * 128 + 512][:rows]
-    Oraw = dump[2 * 128 * 128: 4 * 128 * 128].view(256, 128)[:rows]
-    # expected l and raw O given the kernel's (possibly stale) max m_d
-    c = 1.4426950408889634 * scale
-    Praw = torch.exp2((qf @ kf.T) * c - (m_d * c)[:, None])
-    res["l_relerr"] = ((l_d - Praw.sum(-1)).abs() / Praw.sum(-1)).max().item()
-    Oraw_ref = Praw.to(dt).float() @ vf
-    res["Oraw_maxerr"] = (Oraw - Oraw_ref).abs().max().item()
-    res["Oraw_ref_absmax"] = Oraw_ref.abs().max().item()
-    # whole-tensor check vs SDPA fp32
-    ref = torch.nn.functional.scaled_dot_product_attention(
-        q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)
-    ).transpose(1, 2)
-    res["full_maxerr"] = (o.float() - ref).abs().max().item()
-    res["full_nan"] = bool(torch.isnan(o.float()).any().item())
-    print(json.dumps(res))
+    qf = q[0, :rows, 0].float().cpu()
+    kf = k[0, :, 0].float().cpu()
+    vf = v[0, :, 0].float().cpu()
+    q_img = swizzled_image(q[0, :128, 0].cpu())
+    k_img = swizzled_image(k[0, :128, 0].cpu())
+    ref = None
+    if level >= 4:
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)
+        ).transpose(1, 2).cpu()
+    torch.cuda.synchronize()
+    rc = lib.fa_fwd_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, N, H, D, sb,
+                          sn, sh, code, dump.data_ptr(), knobs, diag.data_ptr())
+    res = {"rc": rc, "level": level}
+    if rc != 0:
+        res["err"] = _lib.last_error()
+    nrec = int(diag[0].item())
+    if nrec:
+        recs = diag[4:4 + 4 * min(nrec, 60)].view(-1, 4).tolist()
+        res["diag"] = [[hex(a & 0xFFFFFFFF), b, c, d] for a, b, c, d in recs[:12]]
+        res["diag_count"] = nrec
+    if level == 2:
+        words = dump.view(torch.int32)
+        res["q_smem_match"] = bool((words[:8192] == q_img).all().item())
+        res["k_smem_match"] = bool((words[8192:16384] == k_img).all().item())
+        res["q_smem_nonzero"] = int((words[:8192] != 0).sum().item())
+    if level >= 3:
+        S0 = qf @ kf[:128].T
+        S_dump = dump[: 2 * 128 * 128].view(256, 128)[:rows]
+        res["S_maxerr"] = (S_dump - S0).abs().max().item()
+        res["S_ref_absmax"] = S0.abs().max().item()
+        res["S_dump_absmax"] = S_dump.abs().max().item()
+    if level >= 4:
+        scale = 1.0 / (D ** 0.5)
+        l_d = dump[4 * 128 * 128: 4 * 128 * 128 + 256][:rows]
+        m_d = dump[4 * 128 * 128 + 256: 4 * 128 * 128 + 512][:rows]
+        Oraw = dump[2 * 128 * 128: 4 * 128 * 128].view(256, 128)[:rows]
+        c = 1.4426950408889634 * scale
+        Praw = torch.exp2((qf @ kf.T) * c - (m_d * c)[:, None])
+        res["l_relerr"] = ((l_d - Praw.sum(-1)).abs() / Praw.sum(-1)).max().item()
+        Oraw_ref = Praw.to(dt).float() @ vf
+        res["Oraw_maxerr"] = (Oraw - Oraw_ref).abs().max().item()
+        res["Oraw_ref_absmax"] = Oraw_ref.abs().max().item()
+        if rc == 0:
+            oc = o.float().cpu()
+            res["full_maxerr"] = (oc - ref).abs().max().item()
+            res["full_nan"] = bool(torch.isnan(oc).any().item())
+    print("RESULT_JSON " + json.dumps(res))
 
 
-def spawn(extra, timeout=90, env=None):
-    cmd = [sys.executable, os.path.abspath(__file__), "--one"] + [str(x) for x in extra]
+def spawn(extra, timeout=90, env=None, prefix=()):
+    cmd = list(prefix) + [sys.executable, os.path.abspath(__file__), "--one"] + [str(x) for x in extra]
     t0 = time.time()
     e = dict(os.environ)
     if env:
         e.update(env)
     try:
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e)
-        out = p.stdout.strip().splitlines()
-        last = out[-1] if out else ""
-        try:
-            js = json.loads(last)
-        except Exception:
-            js = {"raw_stdout": p.stdout[-1500:], "raw_stderr": p.stderr[-1500:], "code": p.returncode}
+        js = None
+        other = []
+        for line in p.stdout.splitlines():
+            if line.startswith("RESULT_JSON "):
+                js = json.loads(line[len("RESULT_JSON "):])
+            else:
+                other.append(line)
+        if js is None:
+            js = {"no_result": True}
+        js["exit"] = p.returncode
+        if other:
+            js["stdout"] = "\n".join(other)[-3000:]
+        if p.stderr.strip():
+            js["stderr"] = p.stderr[-1500:]
         js["secs"] = round(time.time() - t0, 1)
         return js
-    except subprocess.TimeoutExpired:
-        return {"timeout": True, "secs": timeout}
+    except subprocess.TimeoutExpired as ex:
+        return {"timeout": True, "secs": timeout,
+                "stdout": (ex.stdout or b"").decode("utf-8", "replace")[-2000:] if ex.stdout else ""}
 
 
 def main():
@@ -108,7 +148,7 @@ def main():
     ap.add_argument("--B", type=int, default=1)
     ap.add_argument("--N", type=int, default=256)
     ap.add_argument("--H", type=int, default=1)
-    ap.add_argument("--knobs", type=int, nargs=7, default=[16, 1024, 16384, 1024, 2048, 0, 8])
+    ap.add_argument("--knobs", type=int, nargs=8, default=[16, 1024, 16384, 1024, 2048, 0, 8, 4])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bringup.json"))
     args = ap.parse_args()
     if args.one:
@@ -116,10 +156,8 @@ def main():
         return
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    guard = {"FA_SM100_LIB": os.path.join(ROOT, "flash_attention_from_scratch_b200", "csrc",
-                                          "libfa_sm100_guard.so")}
-    if not os.path.exists(guard["FA_SM100_LIB"]):
-        guard = None
+    guard_lib = os.path.join(ROOT, "flash_attention_from_scratch_b200", "csrc", "libfa_sm100_guard.so")
+    guard = {"FA_SM100_LIB": guard_lib} if os.path.exists(guard_lib) else None
     log = []
 
     def rec(name, js):
@@ -135,41 +173,59 @@ def main():
 
     base = ["--dtype", "bf16", "--B", 1, "--N", 256, "--H", 1]
     default = [16, 1024, 16384, 1024, 2048, 0, 8]
-    r = spawn(base + ["--knobs"] + default, env=guard)
-    rec("default", r)
-    good = default if ok(r) else None
-    if not good:
-        s_ok = r.get("rc") == 0 and r.get("S_maxerr", 1e9) < 0.5
-        if not s_ok:
-            # QK^T descriptor variants
-            for lbo, sbo in [(0, 1024), (1024, 1024), (16, 64), (128, 1024), (1024, 16)]:
-                kn = [lbo, sbo] + default[2:]
-                r2 = spawn(base + ["--knobs"] + kn, env=guard)
-                rec(f"qk lbo={lbo} sbo={sbo}", r2)
-                if r2.get("rc") == 0 and r2.get("S_maxerr", 1e9) < 0.5:
-                    default = kn
-                    s_ok = True
-                    if ok(r2):
-                        good = kn
-                    break
-        if s_ok and not good:
+    passed_level = 0
+    for level in (1, 2, 3):
+        r = spawn(base + ["--knobs"] + default + [level], env=guard)
+        rec(f"level{level}", r)
+        good_here = r.get("rc") == 0 and (
+            level == 1 or (level == 2 and r.get("q_smem_match") and r.get("k_smem_match")) or
+            (level == 3 and r.get("S_maxerr", 1e9) < 0.5))
+        if not good_here:
+            break
+        passed_level = level
+    if passed_level == 2:
+        # QK^T descriptor variants
+        for lbo, sbo in [(0, 1024), (1024, 1024), (16, 64), (128, 1024), (1024, 16)]:
+            kn = [lbo, sbo] + default[2:]
+            r2 = spawn(base + ["--knobs"] + kn + [3], env=guard)
+            rec(f"level3 qk lbo={lbo} sbo={sbo}", r2)
+            if r2.get("rc") == 0 and r2.get("S_maxerr", 1e9) < 0.5:
+                default = kn
+                passed_level = 3
+                break
+    good = None
+    if passed_level == 3:
+        r = spawn(base + ["--knobs"] + default + [4], env=guard)
+        rec("level4 default", r)
+        if ok(r):
+            good = default
+        else:
             for v_lbo, v_sbo, kstep, swap, pstep in itertools.product(
                     [16384, 1024], [1024, 16384], [2048, 32], [0, 1], [8, 16]):
                 if v_lbo == v_sbo:
                     continue
                 kn = default[:2] + [v_lbo, v_sbo, kstep, swap, pstep]
-                r2 = spawn(base + ["--knobs"] + kn, env=guard)
-                rec(f"pv lbo={v_lbo} sbo={v_sbo} kstep={kstep} swap={swap} pstep={pstep}", r2)
+                if kn == default:
+                    continue
+                r2 = spawn(base + ["--knobs"] + kn + [4], env=guard)
+                rec(f"level4 pv lbo={v_lbo} sbo={v_sbo} kstep={kstep} swap={swap} pstep={pstep}", r2)
                 if ok(r2):
                     good = kn
                     break
-    rec("RESULT", {"good_knobs": good})
-    if good:
-        for dtype, B, N, H in [("fp16", 1, 256, 1), ("bf16", 2, 512, 3), ("bf16", 1, 128, 2),
-                               ("bf16", 1, 384, 1), ("bf16", 1, 2048, 4), ("fp16", 2, 1024, 16)]:
-            r3 = spawn(["--dtype", dtype, "--B", B, "--N", N, "--H", H, "--knobs"] + good, env=guard)
-            rec(f"shape {dtype} B={B} N={N} H={H}", r3)
+    rec("RESULT", {"good_knobs": good, "passed_level": passed_level})
+    if not good:
+        # one sanitizer pass at the first failing level for a precise fault report
+        lvl = min(passed_level + 1, 4)
+        r = spawn(base + ["--knobs"] + default + [lvl], env=guard, timeout=300,
+                  prefix=["compute-sanitizer", "--tool", "memcheck", "--print-limit", "5"])
+        rec(f"sanitizer level{lvl}", r)
+        return 1
+    for dtype, B, N, H in [("fp16", 1, 256, 1), ("bf16", 2, 512, 3), ("bf16", 1, 128, 2),
+                           ("bf16", 1, 384, 1), ("bf16", 1, 2048, 4), ("fp16", 2, 1024, 16)]:
+        r3 = spawn(["--dtype", dtype, "--B", B, "--N", N, "--H", H, "--knobs"] + good + [4], env=guard)
+        rec(f"shape {dtype} B={B} N={N} H={H}", r3)
+    return 0
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())
