@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- the attention-forward hot path on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is ONE pass of the hot path (one launch of the fused attention forward) over one batch of
+synthetic Q/K/V already resident in HBM.  Workloads (BASELINE.json `configs`):
+
+  headline  bf16 (B=4, N=4096, H=32, d=128) per GPU            -- configs[1], the default
+  dtype16k  fp16|bf16 (8, 8192, 16, 128) per GPU               -- configs[3]  (--dtype fp16)
+  shard16k  bf16 global (8, 16384, 32, 128) split over the ranks -- configs[4] (strong scaling)
+
+With N > 1 (torchrun, one rank per GPU) every rank owns its own (batch x heads) shard and launches
+independently: there is NO collective on the data path; torch.distributed is used only for the
+barrier and the max-over-ranks of the device time.  Default scaling is WEAK: each rank runs the
+per-GPU headline problem (global batch = 4 N).
+
+Prints ONE JSON line (rank 0) with the contract keys plus `roofline`, `cpu_baseline`, `e2e`,
+`clocks`, `gpu_launches`.  `--impl reference` times the reference-side CPU implementation of the
+path (torch CPU attention = the reference's own test oracle family, see oracle/) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "attention TFLOPs @ seq_len=4096 d_head=128; % of B200 bf16 tensor-core peak"
+UNIT = "TFLOP/s"
+
+WORKLOADS = {
+    # name: (B, N, H, d, default dtype, scaling)
+    "headline": (4, 4096, 32, 128, "bf16", "weak"),
+    "dtype16k": (8, 8192, 16, 128, "bf16", "weak"),
+    "shard16k": (8, 16384, 32, 128, "bf16", "strong"),
+}
+
+
+def matmul_flops(B, N, H, D):
+    return 4.0 * B * H * N * N * D  # QK^T + PV, 2 flop per MAC
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    return 1590.0, 1400.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
+
+
+def load_ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_attention_baseline(shape, dtype_name, reps, warmup=1):
+    """Times torch CPU SDPA (all host threads) on `shape`; returns (tflops, cores, seconds/rep)."""
+    import torch
+
+    from oracle import sdpa_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dt = torch.bfloat16 if dtype_name == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(shape, generator=g).to(dt) for _ in range(3))
+    for _ in range(warmup):
+        sdpa_ref(q, k, v)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sdpa_ref(q, k, v)
+    dt_s = (time.perf_counter() - t0) / reps
+    return matmul_flops(*shape) / dt_s / 1e12, cores, dt_s
+
+
+def cpu_sample_shape(B, N, H, D):
+    """Bounded sample of the workload for the CPU arm: one batch entry, at most 32 heads, capped so
+    a rep stays within a few seconds (about 0.3 TFLOP of work)."""
+    h = H
+    while h > 1 and matmul_flops(1, N, h, D) > 0.3e12:
+        h //= 2
+    return (1, N, h, D)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B, N, H, D, _, scaling = WORKLOADS[args.workload]
+    shape = cpu_sample_shape(B, N, H, D)
+    tflops, cores, sec = cpu_attention_baseline(shape, args.dtype, reps=max(1, args.steps),
+                                                warmup=max(1, min(args.warmup, 2)))
+    sample = f"torch CPU SDPA {args.dtype} on (B,N,H,d)={shape} of the {args.workload} workload, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tflops, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {args.dtype} (B,N,H,d)=({B},{N},{H},{D}); each step = "
+                               f"a bounded sample {shape}", "timing": "host wall clock"},
+        "cpu_baseline": {"value": tflops, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default=None, choices=["bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.dtype is None:
+        args.dtype = WORKLOADS[args.workload][4]
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import flash_attention_from_scratch_b200 as fa
+    from flash_attention_from_scratch_b200 import _lib
+    from flash_attention_from_scratch_b200.shard import shard_for_rank
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N, H, D, _, scaling = WORKLOADS[args.workload]
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    if scaling == "weak":
+        gB, gH = B * world, H
+        lB, lH = B, H
+    else:
+        sh = shard_for_rank(B, H, world, rank)
+        gB, gH = B, H
+        lB, lH = sh.batch, sh.heads
+    shape = (lB, N, lH, D)
+    local_flops = matmul_flops(*shape)
+    global_flops = matmul_flops(gB, N, gH, D)
+
+    # two rotating input sets (each set Q+K+V+O = 4 tensors; the headline set is 512 MiB >> 126 MB
+    # L2), so no step starts with its inputs cached by the previous one
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = []
+    for _ in range(2):
+        q, k, v = (torch.randn(shape, device=dev, dtype=dt, generator=gen) for _ in range(3))
+        sets.append((q, k, v, torch.empty_like(q)))
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        q, k, v, o = sets[i & 1]
+        fa.forward(None, q, k, v, o)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step(i)
+        ev[i + 1].record(stream)
+    barrier()
+    launches = _lib.launch_count() - n0
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kern_ms = sum(per_launch_ms) / len(per_launch_ms)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = t.item()
+    ms_per_step = total_ms_max / args.steps
+    value = global_flops / (ms_per_step * 1e-3) / 1e12
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        hq, hk, hv = (torch.empty(shape, dtype=dt).pin_memory() for _ in range(3))
+        for src, dst in zip(sets[0][:3], (hq, hk, hv)):
+            dst.copy_(src)
+        ho = torch.empty(shape, dtype=dt).pin_memory()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            fa.forward_host(hq, hk, hv, ho, device=local_rank)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fa.forward_host(hq, hk, hv, ho, device=local_rank)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        nbytes = hq.numel() * hq.element_size()
+        e2e = {"value": global_flops / te.item() / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
+               "path": "fa_fwd_host (C ABI): pinned host Q,K,V -> HBM, kernel, O -> pinned host; "
+                       "batch-pipelined copies inside the timed region"}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # bounded sample: one batch entry per rep, about 10-20 s of CPU work in total
+        cshape = cpu_sample_shape(B, N, H, D)
+        _, _, probe = cpu_attention_baseline(cshape, args.dtype, reps=1, warmup=1)
+        reps = int(max(3, min(40, 12.0 / max(probe, 1e-3))))
+        tf, cores, sec = cpu_attention_baseline(cshape, args.dtype, reps=reps, warmup=0)
+        cpu = {"value": tf, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"torch CPU SDPA {args.dtype} on (B,N,H,d)={cshape} (1 of {B} batch entries of the "
+                         f"workload per rep), 2 warm-ups + {reps} reps, {sec:.3f} s/rep"}
+
+    if rank == 0:
+        burst, sustained, how = load_peaks()
+        achieved = local_flops / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {args.dtype} fused attention forward, per-GPU (B,N,H,d)="
+                            f"({lB},{N},{lH},{D}), global ({gB},{N},{gH},{D}), non-causal, randn inputs",
+                "flops_per_step": global_flops, "flop_model": "4*B*H*N^2*d",
+                "l2_policy": "inputs larger than L2: two rotating 4-tensor sets (>= 512 MiB each at the "
+                             "headline) so no step re-reads a cached input",
+                "parallelism": f"dp{world} over (batch x heads), no collective on the data path",
+                "timing": "cudaEvents on the launch stream, barrier+synchronize both sides, max over ranks",
+            },
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": UNIT,
+                         "frac": achieved / burst, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, "
+                         f"cuBLAS burst; sustained {sustained})", "frac_of_sustained": achieved / sustained,
+                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": "fa::fa_fwd_kernel",
+                         "kernel_ms": kern_ms, "traffic": load_ncu_traffic()},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,10 +43,26 @@ constexpr int kTmemCols = 512;
 constexpr int kSmemQ = 0;
 constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;
 constexpr int kSmemBar = kSmemKV + kKVStages * kTileBytes;
-constexpr int kNumBarriers = 2 + 2 * kKVStages + 6;
+constexpr int kNumBarriers = 2 + 2 * kKVStages + 8;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
 constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack for manual 1024 B alignment
+
+// Tunables (overridable with -D at build time; tools/build_variants.py sweeps them).
+#ifndef FA_EMU_PAIRS
+#define FA_EMU_PAIRS 4        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
+#endif
+#ifndef FA_EMU_PAIRS_LAST
+#define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
+#endif
+#ifndef FA_SPLIT_P
+#define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
+#endif
+constexpr int kEmuPairs = FA_EMU_PAIRS;
+constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
+constexpr bool kSplitP = FA_SPLIT_P != 0;
+// evenly spread `n` emulated pairs over the 16 pairs of a fragment
+__host__ __device__ constexpr bool emulate_pair(int pair, int n) { return ((pair * n) % 16) < n && n > 0; }
 
 // Lazy rescale threshold in log2 units: O and l are only rescaled when the running max grows by
 // more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in fp32,
@@ -98,6 +114,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     auto s_full = [&](int s) { return bar0 + 8u * (2 + 2 * kKVStages + s); };
     auto p_full = [&](int s) { return bar0 + 8u * (4 + 2 * kKVStages + s); };
     auto o_full = [&](int s) { return bar0 + 8u * (6 + 2 * kKVStages + s); };
+    auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kKVStages + s); };
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
 
     // tile coordinates: q-pair fastest so co-resident CTAs share K/V of one (b, h) in L2
@@ -120,6 +137,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 mbar_init(q_full(s), 1);
                 mbar_init(s_full(s), 1);
                 mbar_init(p_full(s), 4);  // one elected arrive per softmax warp
+                mbar_init(p_last(s), 4);
                 mbar_init(o_full(s), 1);
             }
             for (int i = 0; i < kKVStages; ++i) {
@@ -143,7 +161,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr);
 
     if (wg == 2) {
-        setmaxnreg_dec<104>();
+        setmaxnreg_dec<88>();
         if (warp == 9) {
             // ================================ TMA producer ================================
             if (lane == 0) {
@@ -196,7 +214,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         umma_ss(tmem_base + s * kBlockN, a0 + off, b0 + off, idesc_qk, k > 0);
                     }
                 };
-                auto issue_pv = [&](int s, int slot, bool accumulate) {
+                auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
                     const uint32_t lbo = kDebug ? dbg.v_lbo : (uint32_t)kHalfBytes;
                     const uint32_t sbo = kDebug ? dbg.v_sbo : 1024u;
                     const uint32_t kstep = kDebug ? dbg.v_kstep : 2048u;
@@ -204,7 +222,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     const uint64_t b0 =
                         umma_smem_desc_sw128(smem_base + kSmemKV + slot * kTileBytes, lbo, sbo);
 #pragma unroll
-                    for (int k = 0; k < kBlockN / 16; ++k) {
+                    for (int k = k_begin; k < k_end; ++k) {
                         umma_ts(tmem_base + 2 * kBlockN + s * kHeadDim,
                                 tmem_base + s * kBlockN + k * pstep, b0 + ((k * kstep) >> 4),
                                 idesc_pv, (accumulate || k > 0) ? 1u : 0u);
@@ -247,7 +265,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     for (int s = 0; s < kQStages; ++s) {
                         mbar_wait(p_full(s), j & 1, 230 + s);  // P_s(j) stored, O_s rescaled
                         tc_fence_after();
-                        issue_pv(s, slot_of(it_v), j > 0);
+                        if constexpr (kSplitP) {
+                            issue_pv(s, slot_of(it_v), j > 0, 0, 6);
+                            mbar_wait(p_last(s), j & 1, 250 + s);  // last 32 columns of P_s(j)
+                            tc_fence_after();
+                            issue_pv(s, slot_of(it_v), true, 6, 8);
+                        } else {
+                            issue_pv(s, slot_of(it_v), j > 0, 0, 8);
+                        }
                         if (has_next) {
                             if (s == 0) {
                                 mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
@@ -268,7 +293,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
     } else {
         // ==================================== softmax =====================================
-        setmaxnreg_inc<200>();
+        setmaxnreg_inc<208>();
         const int s = wg;                    // Q tile handled by this warpgroup
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -300,12 +325,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             if constexpr (kDebug) {
                 if (level == 3) break;
             }
-            float mx = m_run;
+            // row max: 8 independent chains (the serial chain would cost 64 x 4 cycles of latency)
+            float mxs[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[q][i]));
+                for (int i = 1; i < 16; ++i) {
+                    mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
+                    mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
+                }
             }
+            float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+            mx = fmaxf(mx, m_run);
             float alpha = 1.f;
             if (j == 0) {
                 m_run = mx;
@@ -331,25 +365,42 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 }
             }
             const float neg_mc = -m_run * c;
-            float sum = 0.f;
+            const float2 c2 = make_float2(c, c);
+            const float2 nm2 = make_float2(neg_mc, neg_mc);
+            float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sr[q][i]), c, neg_mc));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sr[q][i + 1]), c, neg_mc));
-                    sum += p0 + p1;
-                    pk[i >> 1] = (kDebug && dbg.p_swap) ? pack_16x2<kBF16>(p1, p0)
-                                                        : pack_16x2<kBF16>(p0, p1);
+                for (int i = 0; i < 16; ++i) {
+                    const float2 x = __ffma2_rn(
+                        make_float2(__uint_as_float(sr[q][2 * i]), __uint_as_float(sr[q][2 * i + 1])),
+                        c2, nm2);
+                    float2 p;
+                    if (emulate_pair(i, q == 3 ? kEmuPairsLast : kEmuPairs)) {
+                        p = ex2_emulated_x2(x);
+                    } else {
+                        p.x = ex2_approx(x.x);
+                        p.y = ex2_approx(x.y);
+                    }
+                    if (i & 1) sum_a = __fadd2_rn(sum_a, p);
+                    else sum_b = __fadd2_rn(sum_b, p);
+                    pk[i] = (kDebug && dbg.p_swap) ? pack_16x2<kBF16>(p.y, p.x)
+                                                   : pack_16x2<kBF16>(p.x, p.y);
                 }
                 tmem_st_32x32b_x16(t_p + q * 16, pk);
+                if (kSplitP && q == 2) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_full(s));
+                }
             }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full(s));
-            l_run = l_run * alpha + sum;
+            if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
+            l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
         }
 
         // --------------------------------- epilogue --------------------------------------

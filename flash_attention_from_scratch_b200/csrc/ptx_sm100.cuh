@@ -298,6 +298,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// exp2 of two values on the FMA pipe (no MUFU): Cody-Waite split with the 2^23+2^22 magic-number
+// trick (round-down add leaves floor(x) in the low mantissa bits), degree-3 minimax polynomial for
+// 2^f on [0,1) (max rel. error 8.6e-5, coefficients fitted for this kernel: p(0) = 1 exactly),
+// then the integer part is added straight into the exponent field.  Requires x <= 127; inputs
+// below -127 are clamped (result ~ 2^-127 ~ 0).  Accuracy is far below the 2^-9 (bf16) / 2^-11
+// (fp16) rounding P receives anyway.
+__device__ __forceinline__ float2 ex2_emulated_x2(float2 x) {
+    const float kMagic = 12582912.0f;  // 2^23 + 2^22
+    x.x = fmaxf(x.x, -127.0f);
+    x.y = fmaxf(x.y, -127.0f);
+    const float2 t = __fadd2_rd(x, make_float2(kMagic, kMagic));        // low bits = floor(x)
+    const float2 r = __fadd2_rn(t, make_float2(-kMagic, -kMagic));      // floor(x) as float
+    const float2 f = __fadd2_rn(x, make_float2(-r.x, -r.y));            // fractional part in [0,1)
+    float2 p = __ffma2_rn(make_float2(0.07706724f, 0.07706724f), f,
+                          make_float2(0.22764498f, 0.22764498f));
+    p = __ffma2_rn(p, f, make_float2(0.69511664f, 0.69511664f));
+    p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+    float2 out;
+    out.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+    out.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+    return out;
+}
+
 // Packs two fp32 into one 32-bit register of two 16-bit floats: lo -> bits [0,16), hi -> [16,32).
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {

@@ -1,0 +1,234 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the reference-facing
+operator and the C ABI, against the oracle.
+
+Tolerances (written here as the north star states them, BASELINE.json):
+  * allclose(out, SDPA, rtol=1e-2, atol=1e-3) for seq_len >= 512 (atol 2e-3 below, see
+    tests/test_oracle.py::north_star_tol), for bf16 AND fp16;
+  * the reference's own criterion  max|out - ref16| <= 2 * max|ref16 - ref32|
+    (/root/reference/py/flash_helpers/test/test.py:58-61).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import flash_attention
+from flash_helpers.kernel_configs import DType, FlashForwardKernelConfig, get_kernels_to_build
+from flash_helpers.test.utils import BATCH_SIZE_FOR_SEQ_LEN, BENCHMARK_N_HEADS, QKVConfig, generate_qkv
+from oracle import blockwise_kernel_ref, py_flash_attention, reference_pass_criterion, sdpa_ref
+from test_oracle import north_star_tol
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+DTYPES = {torch.bfloat16: DType.BF16, torch.float16: DType.FP16}
+
+
+def cfg_for(dtype):
+    return FlashForwardKernelConfig(dtype=DTYPES[dtype])
+
+
+def rand_qkv(shape, dtype, seed=0, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return tuple((torch.randn(shape, device=DEV, dtype=torch.float32, generator=g) * scale).to(dtype)
+                 for _ in range(3))
+
+
+def sdpa32(q, k, v):
+    return sdpa_ref(q.float(), k.float(), v.float())
+
+
+# ------------------------------------------------------------------ golden fixtures (reference-made)
+def test_golden_fixtures(golden):
+    q, k, v = (golden[n].to(DEV) for n in "qkv")
+    out = flash_attention.forward(cfg_for(q.dtype), q, k, v).cpu()
+    ok, d_out, d_ref = reference_pass_criterion(out, golden["ref16"], golden["ref32"])
+    assert ok, (d_out, d_ref)
+    torch.testing.assert_close(out.float(), golden["ref32"].float(), **north_star_tol(q.shape[1]))
+    # and against the block-wise restatement of the kernel arithmetic (lazy rescale included)
+    blk = blockwise_kernel_ref(golden["q"], golden["k"], golden["v"], block=128, rescale_threshold=8.0)
+    eps = 2 ** -8 if q.dtype == torch.bfloat16 else 2 ** -11
+    assert (out.float() - blk.float()).abs().max().item() <= 2 * eps * max(1.0, blk.float().abs().max().item())
+
+
+# ------------------------------------------------------------------ seeded shapes, both dtypes
+SHAPES = [(1, 128, 2), (1, 256, 1), (2, 384, 3), (2, 512, 16), (1, 1024, 32), (3, 640, 5),
+          (1, 2048, 4), (2, 1152, 7)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,N,H", SHAPES)
+def test_matches_sdpa(dtype, B, N, H):
+    q, k, v = rand_qkv((B, N, H, 128), dtype, seed=B * 1000 + N + H)
+    out = flash_attention.forward(cfg_for(dtype), q, k, v)
+    ref32 = sdpa32(q, k, v)
+    torch.testing.assert_close(out.float(), ref32, **north_star_tol(N))
+    ref16 = py_flash_attention(q, k, v, upcast=False)
+    ok, d_out, d_ref = reference_pass_criterion(out, ref16, py_flash_attention(q, k, v, upcast=True))
+    assert ok, (d_out, d_ref)
+
+
+# ------------------------------------------------------------------ the reference's own test, verbatim shape
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_reference_suite_shape_and_criterion(dtype):
+    # py/flash_helpers/test/test.py:19-61: (16, 2048, 16, 128), every config of get_kernels_to_build()
+    seq_len = 2048
+    cfg = QKVConfig(n_heads=BENCHMARK_N_HEADS, d_head=128, batch_size=BATCH_SIZE_FOR_SEQ_LEN[seq_len],
+                    seq_len=seq_len, dtype=dtype, device=DEV)
+    q, k, v = generate_qkv(cfg, seed=1234)
+    ref16 = py_flash_attention(q, k, v, upcast=False)
+    ref32 = py_flash_attention(q, k, v, upcast=True)
+    for kcfg in get_kernels_to_build():
+        if kcfg.dtype.to_torch_dtype() != dtype:
+            continue
+        out = flash_attention.forward(kcfg, q, k, v)
+        diff = (out - ref16).abs().max().item()
+        assert diff <= 2 * (ref16 - ref32).abs().max().item()
+        torch.testing.assert_close(out.float(), ref32.float(), rtol=1e-2, atol=1e-3)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes: properties
+def test_headline_shape_properties():
+    B, N, H = 4, 4096, 32
+    q, k, v = rand_qkv((B, N, H, 128), torch.bfloat16, seed=0)
+    out = flash_attention.forward(None, q, k, v)
+    assert torch.isfinite(out.float()).all()
+    # (1) vs torch SDPA in the same dtype on the full tensor (north-star tolerance)
+    ref = sdpa_ref(q, k, v)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2, atol=1e-3)
+    # (2) fp32 oracle on a slice
+    torch.testing.assert_close(out[1:2, :, 5:7].float(), sdpa32(q[1:2, :, 5:7], k[1:2, :, 5:7], v[1:2, :, 5:7]),
+                               rtol=1e-2, atol=1e-3)
+    # (3) (batch, head) problems are independent: a sub-problem computed alone is BIT-identical
+    sub = flash_attention.forward(None, q[2:3, :, 8:16].contiguous(), k[2:3, :, 8:16].contiguous(),
+                                  v[2:3, :, 8:16].contiguous())
+    assert torch.equal(sub, out[2:3, :, 8:16])
+    # (4) determinism
+    assert torch.equal(out, flash_attention.forward(None, q, k, v))
+    # (5) V = 1  =>  O = sum(rn16(P)) / sum(P) = 1 up to the rounding of P
+    ones = torch.ones_like(v)
+    o1 = flash_attention.forward(None, q, k, ones).float()
+    assert (o1 - 1).abs().max().item() <= 2 ** -8
+    # (6) K = 0 => uniform attention: O = column mean of V
+    mean_v = v.float().mean(dim=1, keepdim=True).expand(-1, N, -1, -1)
+    o2 = flash_attention.forward(None, q, torch.zeros_like(k), v).float()
+    torch.testing.assert_close(o2, mean_v, rtol=1e-2, atol=1e-3)
+
+
+def test_key_permutation_invariance():
+    B, N, H = 1, 4096, 4
+    q, k, v = rand_qkv((B, N, H, 128), torch.bfloat16, seed=3)
+    perm = torch.randperm(N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
+    a = flash_attention.forward(None, q, k, v).float()
+    b = flash_attention.forward(None, q, k[:, perm].contiguous(), v[:, perm].contiguous()).float()
+    torch.testing.assert_close(a, b, rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,B", [(8192, 8), (16384, 1)])
+def test_long_sequences_fp16_vs_bf16(N, B):
+    # BASELINE.json configs[3]: fp16 vs bf16 at seq_len 8192 (fp16 must be the tighter one)
+    H = 16 if N == 8192 else 2
+    errs = {}
+    for dtype in (torch.bfloat16, torch.float16):
+        q, k, v = rand_qkv((B, N, H, 128), dtype, seed=11)
+        out = flash_attention.forward(cfg_for(dtype), q, k, v)
+        sl = (slice(0, 1), slice(None), slice(0, 2))
+        ref = sdpa32(q[sl], k[sl], v[sl])
+        torch.testing.assert_close(out[sl].float(), ref, rtol=1e-2, atol=1e-3)
+        errs[dtype] = (out[sl].float() - ref).abs().max().item()
+    assert errs[torch.float16] < errs[torch.bfloat16]
+
+
+# ------------------------------------------------------------------ edge cases
+def test_rescale_path_growing_scores():
+    # scores that keep growing along the key axis: every KV block raises the row max by far more
+    # than the lazy-rescale threshold, so the O/l rescale path runs on every block
+    N = 1024
+    g = torch.Generator(device=DEV).manual_seed(5)
+    q = torch.randn(1, N, 2, 128, device=DEV, generator=g)
+    k = q.mean(1, keepdim=True).sign() * torch.linspace(0, 6, N, device=DEV).view(1, N, 1, 1) \
+        + torch.randn(1, N, 2, 128, device=DEV, generator=g) * 0.5
+    v = torch.randn(1, N, 2, 128, device=DEV, generator=g)
+    for dtype in (torch.bfloat16, torch.float16):
+        qq, kk, vv = (t.to(dtype) for t in (q * 2, k, v))
+        out = flash_attention.forward(None, qq, kk, vv)
+        assert torch.isfinite(out.float()).all()
+        ok, d_out, d_ref = reference_pass_criterion(out, py_flash_attention(qq, kk, vv, False),
+                                                    py_flash_attention(qq, kk, vv, True))
+        assert ok, (dtype, d_out, d_ref)
+
+
+def test_large_magnitude_and_constant_inputs():
+    q, k, v = rand_qkv((1, 512, 2, 128), torch.bfloat16, seed=9, scale=6.0)   # |S| up to ~1e3 * ...
+    out = flash_attention.forward(None, q, k, v)
+    assert torch.isfinite(out.float()).all()
+    ok, d_out, d_ref = reference_pass_criterion(out, py_flash_attention(q, k, v, False),
+                                                py_flash_attention(q, k, v, True))
+    assert ok, (d_out, d_ref)
+    # all rows identical -> every output row equals the (identical) V row mix; zeros stay zeros
+    z = torch.zeros(1, 256, 1, 128, device=DEV, dtype=torch.float16)
+    assert torch.equal(flash_attention.forward(None, z, z, z), z)
+
+
+def test_out_param_stream_and_timed():
+    q, k, v = rand_qkv((2, 512, 4, 128), torch.float16, seed=2)
+    ref = flash_attention.forward(None, q, k, v)
+    o = torch.empty_like(q)
+    ret = flash_attention.forward(cfg_for(torch.float16), q, k, v, o)
+    assert ret.data_ptr() == o.data_ptr() and torch.equal(o, ref)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        o2 = flash_attention.forward(None, q, k, v)
+    st.synchronize()
+    assert torch.equal(o2, ref)
+    o3, ms = flash_attention.forward_timed(None, q, k, v)
+    assert torch.equal(o3, ref) and 0.0 < ms < 100.0
+
+
+def test_operator_errors_match_reference():
+    q, k, v = rand_qkv((1, 256, 2, 128), torch.bfloat16)
+    with pytest.raises(RuntimeError, match="dtype does not match"):
+        flash_attention.forward(cfg_for(torch.float16), q, k, v)
+    with pytest.raises(RuntimeError, match="same data type"):
+        flash_attention.forward(None, q, k.half(), v)
+    with pytest.raises(RuntimeError, match="Only fp16 and bf16"):
+        flash_attention.forward(None, q.float(), k.float(), v.float())
+    with pytest.raises(RuntimeError, match="contiguous"):
+        flash_attention.forward(None, q.transpose(1, 2), k, v)
+    with pytest.raises(RuntimeError, match="same shape"):
+        flash_attention.forward(None, q, k[:, :128].contiguous(), v)
+    with pytest.raises(RuntimeError, match="multiples of B_r"):
+        flash_attention.forward(None, q[:, :192].contiguous(), k[:, :192].contiguous(), v[:, :192].contiguous())
+    with pytest.raises(RuntimeError, match="not found"):
+        flash_attention.forward(None, q[..., :64].contiguous(), k[..., :64].contiguous(), v[..., :64].contiguous())
+
+
+def test_c_abi_strided_heads(lib):
+    # the C ABI takes runtime strides: a head-slice VIEW (what head-sharding produces) works
+    from flash_attention_from_scratch_b200 import _lib
+    q, k, v = rand_qkv((2, 512, 8, 128), torch.bfloat16, seed=4)
+    o = torch.zeros_like(q)
+    qs, ks, vs, os_ = (t[:, :, 2:5] for t in (q, k, v, o))
+    sb, sn, sh, _ = qs.stride()
+    rc = lib.fa_fwd(qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), os_.data_ptr(), 2, 512, 3, 128,
+                    sb, sn, sh, 15, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    ref = flash_attention.forward(None, qs.contiguous(), ks.contiguous(), vs.contiguous())
+    assert torch.equal(os_.contiguous(), ref)
+    assert (o[:, :, :2] == 0).all() and (o[:, :, 5:] == 0).all()
+
+
+def test_host_buffer_entry_equals_device_path():
+    g = torch.Generator().manual_seed(8)
+    q, k, v = (torch.randn(3, 512, 4, 128, generator=g).bfloat16().pin_memory() for _ in range(3))
+    o_host = flash_attention.forward_host(q, k, v)
+    o_dev = flash_attention.forward(None, q.to(DEV), k.to(DEV), v.to(DEV)).cpu()
+    assert torch.equal(o_host, o_dev)
+
+
+def test_launch_counter_counts_our_kernel(lib):
+    from flash_attention_from_scratch_b200 import _lib
+    q, k, v = rand_qkv((1, 256, 1, 128), torch.bfloat16)
+    n0 = _lib.launch_count()
+    flash_attention.forward(None, q, k, v)
+    assert _lib.launch_count() == n0 + 1

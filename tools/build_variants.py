@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Builds tuning variants of libfa_sm100.so (different -D knobs) into csrc/variants/ so one GPU
+round trip can time all of them (tools/sweep_variants.py).  Development aid."""
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
+
+VARIANTS = {
+    # name: defines
+    "emu4": {"FA_EMU_PAIRS": 4},
+    "emu0": {"FA_EMU_PAIRS": 0},
+    "emu0_nosplit": {"FA_EMU_PAIRS": 0, "FA_SPLIT_P": 0},
+    "emu2": {"FA_EMU_PAIRS": 2},
+    "emu6": {"FA_EMU_PAIRS": 6},
+    "emu8": {"FA_EMU_PAIRS": 8},
+    "emu4_last4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
+    "emu6_last4": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 4},
+    "emu4_nosplit": {"FA_EMU_PAIRS": 4, "FA_SPLIT_P": 0},
+}
+
+
+def main():
+    names = sys.argv[1:] or list(VARIANTS)
+    out_dir = fa_build.CSRC / "variants"
+    out_dir.mkdir(exist_ok=True)
+
+    def one(name):
+        flags = tuple(f"-D{k}={v}" for k, v in VARIANTS[name].items())
+        path = fa_build.build(force=True, extra_flags=flags, out=out_dir / f"libfa_{name}.so")
+        return name, path
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for name, path in ex.map(one, names):
+            print(name, path)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Times every library variant under csrc/variants/ on the given shapes (one subprocess each)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shapes", default="4,4096,32")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "sweep.json"))
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    vdir = ROOT / "flash_attention_from_scratch_b200" / "csrc" / "variants"
+    rows = []
+    for lib in sorted(vdir.glob("libfa_*.so")):
+        name = lib.stem[len("libfa_"):]
+        if args.only and name not in args.only.split(","):
+            continue
+        env = dict(os.environ, FA_SM100_LIB=str(lib))
+        p = subprocess.run([sys.executable, str(ROOT / "tools" / "quick_bench.py"), "--shapes", args.shapes,
+                            "--reps", str(args.reps), "--check"], capture_output=True, text=True, env=env,
+                           timeout=300)
+        for line in p.stdout.splitlines():
+            try:
+                r = json.loads(line)
+            except Exception:  # noqa: BLE001
+                continue
+            r["variant"] = name
+            rows.append(r)
+            print(f"{name:16s} {r['shape']} mean {r['tflops_mean']:.1f} best {r['tflops_best']:.1f} TF/s  "
+                  f"maxdiff16 {r.get('maxdiff_vs_sdpa16')}", flush=True)
+        if p.returncode != 0:
+            print(name, "FAILED", p.stderr[-500:], flush=True)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
