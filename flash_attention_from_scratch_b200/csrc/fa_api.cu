@@ -194,10 +194,10 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     prm.seq_len = p.N;
     prm.n_heads = p.H;
     prm.n_kv_blocks = p.N / fa::kBlockN;
-    prm.n_q_pairs = (p.N + fa::kQStages * fa::kBlockM - 1) / (fa::kQStages * fa::kBlockM);
+    prm.n_q_tiles = p.N / fa::kBlockM;
     prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
 
-    const long long n_ctas = 1LL * p.B * p.H * prm.n_q_pairs;
+    const long long n_ctas = 1LL * p.B * p.H * prm.n_q_tiles;
     if (n_ctas > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld CTAs", n_ctas);
     dim3 grid((unsigned)n_ctas), block(fa::kNumThreads);
     if (p.dtype == FA_DTYPE_BF16)
@@ -251,7 +251,7 @@ int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_c
 int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_cols) {
     if (smem_bytes) *smem_bytes = fa::kSmemLaunchBytes;
     if (threads) *threads = fa::kNumThreads;
-    if (rows_per_cta) *rows_per_cta = fa::kQStages * fa::kBlockM;
+    if (rows_per_cta) *rows_per_cta = fa::kBlockM;
     if (tmem_cols) *tmem_cols = fa::kTmemCols;
     return FA_OK;
 }
@@ -302,14 +302,7 @@ int fa_fwd_debug(const void* q, const void* k, const void* v, void* o, int batch
     if (rc != FA_OK) return rc;
     fa::FwdDebug dbg{};
     dbg.dump = dump;
-    dbg.qk_lbo = knobs ? knobs[0] : 16;
-    dbg.qk_sbo = knobs ? knobs[1] : 1024;
-    dbg.v_lbo = knobs ? knobs[2] : fa::kHalfBytes;
-    dbg.v_sbo = knobs ? knobs[3] : 1024;
-    dbg.v_kstep = knobs ? knobs[4] : 2048;
-    dbg.p_swap = knobs ? knobs[5] : 0;
-    dbg.p_col_step = knobs ? knobs[6] : 8;
-    dbg.level = knobs ? knobs[7] : 4;
+    dbg.level = knobs ? knobs[7] : 4;  // knobs[0..6] were descriptor experiments of generation 2
     dbg.diag = diag;
     rc = launch<true>(p, nullptr, dbg);
     if (rc != FA_OK) return rc;

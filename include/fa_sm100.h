@@ -80,9 +80,9 @@ int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_c
 int64_t fa_launch_count(void);
 
 /* Bring-up entry: runs the debug instantiation with explicit descriptor knobs and a dump buffer
- * (see FwdDebug in csrc/fa_fwd_sm100.cuh).  knobs = {qk_lbo, qk_sbo, v_lbo, v_sbo, v_kstep,
- * p_swap, p_col_step, level}; `dump` and `diag` should be host-mapped (pinned) so they survive a
- * trapped kernel.  Synchronous.  Not part of the reference interface. */
+ * (see FwdDebug in csrc/fa_fwd_sm100.cuh).  knobs[7] = bring-up level (1 setup only, 2 TMA,
+ * 3 QK^T, >= 4 everything; knobs[0..6] are ignored); `dump` and `diag` should be host-mapped
+ * (pinned) so they survive a trapped kernel.  Synchronous.  Not part of the reference interface. */
 int fa_fwd_debug(const void* q, const void* k, const void* v, void* o, int batch, int seq_len,
                  int n_heads, int d_head, int64_t stride_batch, int64_t stride_seq,
                  int64_t stride_head, int dtype, float* dump, const uint32_t* knobs,

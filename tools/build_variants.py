@@ -12,15 +12,11 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "emu4": {"FA_EMU_PAIRS": 4},
     "emu0": {"FA_EMU_PAIRS": 0},
-    "emu0_nosplit": {"FA_EMU_PAIRS": 0, "FA_SPLIT_P": 0},
     "emu2": {"FA_EMU_PAIRS": 2},
+    "emu4": {"FA_EMU_PAIRS": 4},
     "emu6": {"FA_EMU_PAIRS": 6},
     "emu8": {"FA_EMU_PAIRS": 8},
-    "emu4_last4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
-    "emu6_last4": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 4},
-    "emu4_nosplit": {"FA_EMU_PAIRS": 4, "FA_SPLIT_P": 0},
 }
 
 

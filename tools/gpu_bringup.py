@@ -22,7 +22,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-DUMP_WORDS = 4 * 128 * 128 + 512
+DUMP_WORDS = 128 * 128 + 512 + 1024
 
 
 def swizzled_image(t):
@@ -89,22 +89,24 @@ def run_one(args):
         res["k_smem_match"] = bool((words[8192:16384] == k_img).all().item())
         res["q_smem_nonzero"] = int((words[:8192] != 0).sum().item())
     if level >= 3:
-        S0 = qf @ kf[:128].T
-        S_dump = dump[: 2 * 128 * 128].view(256, 128)[:rows]
+        S0 = (qf @ kf[:128].T)[:128]
+        S_dump = dump[: 128 * 128].view(128, 128)
         res["S_maxerr"] = (S_dump - S0).abs().max().item()
         res["S_ref_absmax"] = S0.abs().max().item()
         res["S_dump_absmax"] = S_dump.abs().max().item()
     if level >= 4:
         scale = 1.0 / (D ** 0.5)
-        l_d = dump[4 * 128 * 128: 4 * 128 * 128 + 256][:rows]
-        m_d = dump[4 * 128 * 128 + 256: 4 * 128 * 128 + 512][:rows]
-        Oraw = dump[2 * 128 * 128: 4 * 128 * 128].view(256, 128)[:rows]
         c = 1.4426950408889634 * scale
-        Praw = torch.exp2((qf @ kf.T) * c - (m_d * c)[:, None])
-        res["l_relerr"] = ((l_d - Praw.sum(-1)).abs() / Praw.sum(-1)).max().item()
-        Oraw_ref = Praw.to(dt).float() @ vf
-        res["Oraw_maxerr"] = (Oraw - Oraw_ref).abs().max().item()
-        res["Oraw_ref_absmax"] = Oraw_ref.abs().max().item()
+        m_d = dump[128 * 128: 128 * 128 + 256].view(2, 128)
+        l_d = dump[128 * 128 + 256: 128 * 128 + 512].view(2, 128)
+        Sall = (qf[:128] @ kf.T)                                    # rows of CTA 0
+        nb = N // 128
+        worst = 0.0
+        for g in range(2):
+            cols = torch.cat([torch.arange(128 * j + 64 * g, 128 * j + 64 * g + 64) for j in range(nb)])
+            Pg = torch.exp2(Sall[:, cols] * c - (m_d[g] * c)[:, None])
+            worst = max(worst, ((l_d[g] - Pg.sum(-1)).abs() / Pg.sum(-1)).max().item())
+        res["l_relerr"] = worst
         if rc == 0:
             oc = o.float().cpu()
             res["full_maxerr"] = (oc - ref).abs().max().item()
@@ -171,58 +173,28 @@ def main():
     def ok(js):
         return js.get("rc") == 0 and not js.get("full_nan", True) and js.get("full_maxerr", 1) < 2e-2
 
-    base = ["--dtype", "bf16", "--B", 1, "--N", 256, "--H", 1]
-    default = [16, 1024, 16384, 1024, 2048, 0, 8]
+    base = ["--dtype", "bf16", "--B", 1, "--N", 512, "--H", 1]
+    default = [0, 0, 0, 0, 0, 0, 0]
     passed_level = 0
-    for level in (1, 2, 3):
+    for level in (1, 2, 3, 4):
         r = spawn(base + ["--knobs"] + default + [level], env=guard)
         rec(f"level{level}", r)
         good_here = r.get("rc") == 0 and (
             level == 1 or (level == 2 and r.get("q_smem_match") and r.get("k_smem_match")) or
-            (level == 3 and r.get("S_maxerr", 1e9) < 0.5))
+            (level == 3 and r.get("S_maxerr", 1e9) < 0.5) or (level == 4 and ok(r)))
         if not good_here:
             break
         passed_level = level
-    if passed_level == 2:
-        # QK^T descriptor variants
-        for lbo, sbo in [(0, 1024), (1024, 1024), (16, 64), (128, 1024), (1024, 16)]:
-            kn = [lbo, sbo] + default[2:]
-            r2 = spawn(base + ["--knobs"] + kn + [3], env=guard)
-            rec(f"level3 qk lbo={lbo} sbo={sbo}", r2)
-            if r2.get("rc") == 0 and r2.get("S_maxerr", 1e9) < 0.5:
-                default = kn
-                passed_level = 3
-                break
-    good = None
-    if passed_level == 3:
-        r = spawn(base + ["--knobs"] + default + [4], env=guard)
-        rec("level4 default", r)
-        if ok(r):
-            good = default
-        else:
-            for v_lbo, v_sbo, kstep, swap, pstep in itertools.product(
-                    [16384, 1024], [1024, 16384], [2048, 32], [0, 1], [8, 16]):
-                if v_lbo == v_sbo:
-                    continue
-                kn = default[:2] + [v_lbo, v_sbo, kstep, swap, pstep]
-                if kn == default:
-                    continue
-                r2 = spawn(base + ["--knobs"] + kn + [4], env=guard)
-                rec(f"level4 pv lbo={v_lbo} sbo={v_sbo} kstep={kstep} swap={swap} pstep={pstep}", r2)
-                if ok(r2):
-                    good = kn
-                    break
-    rec("RESULT", {"good_knobs": good, "passed_level": passed_level})
-    if not good:
-        # one sanitizer pass at the first failing level for a precise fault report
-        lvl = min(passed_level + 1, 4)
+    rec("RESULT", {"passed_level": passed_level})
+    if passed_level < 4:
+        lvl = passed_level + 1
         r = spawn(base + ["--knobs"] + default + [lvl], env=guard, timeout=300,
                   prefix=["compute-sanitizer", "--tool", "memcheck", "--print-limit", "5"])
         rec(f"sanitizer level{lvl}", r)
         return 1
     for dtype, B, N, H in [("fp16", 1, 256, 1), ("bf16", 2, 512, 3), ("bf16", 1, 128, 2),
                            ("bf16", 1, 384, 1), ("bf16", 1, 2048, 4), ("fp16", 2, 1024, 16)]:
-        r3 = spawn(["--dtype", dtype, "--B", B, "--N", N, "--H", H, "--knobs"] + good + [4], env=guard)
+        r3 = spawn(["--dtype", dtype, "--B", B, "--N", N, "--H", H, "--knobs"] + default + [4], env=guard)
         rec(f"shape {dtype} B={B} N={N} H={H}", r3)
     return 0
 
