@@ -194,12 +194,15 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     prm.seq_len = p.N;
     prm.n_heads = p.H;
     prm.n_kv_blocks = p.N / fa::kBlockN;
-    prm.n_q_tiles = p.N / fa::kBlockM;
+    prm.n_q_pairs = (p.N + fa::kQStages * fa::kBlockM - 1) / (fa::kQStages * fa::kBlockM);
     prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
 
-    const long long n_ctas = 1LL * p.B * p.H * prm.n_q_tiles;
-    if (n_ctas > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld CTAs", n_ctas);
-    dim3 grid((unsigned)n_ctas), block(fa::kNumThreads);
+    const long long n_tiles = 1LL * p.B * p.H * prm.n_q_pairs;
+    if (n_tiles > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld tiles", n_tiles);
+    prm.n_tiles = static_cast<int>(n_tiles);
+    // persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
+    dim3 grid((unsigned)(n_tiles < n_sms ? n_tiles : n_sms)), block(fa::kNumThreads);
     if (p.dtype == FA_DTYPE_BF16)
         fa::fa_fwd_kernel<true, kDebug>
             <<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
@@ -251,7 +254,7 @@ int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_c
 int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_cols) {
     if (smem_bytes) *smem_bytes = fa::kSmemLaunchBytes;
     if (threads) *threads = fa::kNumThreads;
-    if (rows_per_cta) *rows_per_cta = fa::kBlockM;
+    if (rows_per_cta) *rows_per_cta = fa::kQStages * fa::kBlockM;
     if (tmem_cols) *tmem_cols = fa::kTmemCols;
     return FA_OK;
 }

@@ -6,26 +6,25 @@
 // (/root/reference/src/include/softmax.cuh:15-128, forward_kernel.cuh:150-152):
 //     c = log2(e)/sqrt(d);  m = running row max of raw S;  P = exp2(S*c - m*c) in fp32;
 //     l += rowsum(P) (un-rounded fp32);  O += rn16(P) V (fp32 accumulate);  out = rn16(O / l)
-// but a different machine mapping -- nothing of the mma.sync / ldmatrix / cp.async path is kept.
+// but a different machine mapping -- nothing of the mma.sync / ldmatrix / cp.async path is kept:
 //
-// Kernel generation 3 (see profiles/r01_v2_ncu_notes.md for why):
-//   * one CTA = one Q tile of 128 rows of one (batch, head); 1 CTA per SM, 384 threads
-//   * TMA (cp.async.bulk.tensor, 128B swizzle) stages Q once and K/V blocks of 128 rows through a
-//     ring of 6 shared-memory slots guarded by full/empty mbarriers
-//   * one thread issues tcgen05.mma.  S is DOUBLE-BUFFERED in tensor memory across consecutive KV
-//     blocks, so S(j+2) = Q K_{j+2}^T is computed while the softmax of block j+1 runs and the
-//     softmax never waits for the tensor pipe (generation 2 aliased P onto the only S buffer of a
-//     tile, which made the loop softmax -> PV -> next S latency bound at 62 % tensor activity):
-//       TMEM columns [0,128) S[0], [128,256) S[1], [256,384) O_0, [384,512) O_1
-//   * the two softmax warpgroups split every KV block by KEYS: warpgroup g owns key columns
-//     [64g, 64g+64) of each block, with its own running max m_g, row sum l_g and accumulator O_g
-//     (O_g += P_g V[64g:64g+64]); no cross-warpgroup exchange inside the loop.  One thread per row:
-//     tcgen05.ld S, fp32 row max, exp2 (MUFU + a tunable share on the FMA pipe), fp32 row sum,
-//     P written back as packed 16-bit over the first 32 columns of its own S half, lazy rescale
-//     of O_g (only when the max grew by more than 2^8).
-//   * epilogue: the two partial results are merged like split-KV attention,
-//       m = max(m_0, m_1), a_g = 2^((m_g - m) c), out = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1),
-//     rounded to 16 bit, staged in swizzled shared memory and written with TMA.
+//   * PERSISTENT: one CTA per SM walks a static list of work tiles (tile = 2 Q tiles of 128 rows =
+//     256 query rows of one (batch, head); consecutive tiles share K/V in L2).  Loads, MMAs and
+//     the epilogue of neighbouring tiles overlap: the TMA producer and the MMA issuer run ahead
+//     into the next tile while the softmax warpgroups finish the current one.
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) stages Q tiles and K/V blocks through shared
+//     memory guarded by full/empty mbarriers (K/V: ring of 4 x 32 KiB slots).
+//   * one thread issues tcgen05.mma: S_s = Q_s K_j^T (operands from smem) and O_s += P_s V_j
+//     (P read from tensor memory, V from smem, MN-major); accumulators in TMEM:
+//       columns [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1
+//   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
+//     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit in two
+//     parts (96 + 32 columns) so PV starts early, lazy rescale of O (only when the row max grew
+//     by more than 2^8), final 1/l scaling and TMA store of O through swizzled shared memory.
+//   The two Q tiles ping-pong: while the tensor core runs PV_1(j-1) and S_1(j) the softmax
+//   warpgroup 0 works on S_0(j), and vice versa.
+//
+// Generations 1-3 and the measurements that led here: profiles/r01_*_notes.md.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -36,21 +35,21 @@
 
 namespace fa {
 
-constexpr int kBlockM = 128;   // query rows per CTA == TMEM lanes
+constexpr int kBlockM = 128;   // query rows per Q tile == TMEM lanes
 constexpr int kBlockN = 128;   // key/value rows per block
 constexpr int kHeadDim = 128;  // d_head (the only one the reference supports, README.md:9-15)
-constexpr int kKeySplit = 2;   // softmax warpgroups; each owns kBlockN / kKeySplit keys of a block
-constexpr int kKeysPerWG = kBlockN / kKeySplit;
-constexpr int kKVStages = 6;   // K/V ring slots (each slot holds one K block or one V block)
+constexpr int kQStages = 2;    // Q tiles per work tile
+constexpr int kKVStages = 4;   // K/V ring slots (each slot holds one K block or one V block)
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
 constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
 constexpr int kTmemCols = 512;
 
-constexpr int kSmemQ = 0;
-constexpr int kSmemKV = kSmemQ + kTileBytes;
-constexpr int kSmemBar = kSmemKV + kKVStages * kTileBytes;
-constexpr int kNumBarriers = 1 + 2 * kKVStages + 2 + 4 + 2;
+constexpr int kSmemQ = 0;                                       // Q_0, Q_1
+constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;         // K/V ring
+constexpr int kSmemStage = kSmemKV + kKVStages * kTileBytes;    // O staging: 16 KiB per Q tile
+constexpr int kSmemBar = kSmemStage + kQStages * kHalfBytes;
+constexpr int kNumBarriers = 4 + 2 * kKVStages + 10;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
 constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack for manual 1024 B alignment
@@ -58,24 +57,39 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 
 // Tunables (overridable with -D at build time; tools/build_variants.py sweeps them).
 #ifndef FA_EMU_PAIRS
-#define FA_EMU_PAIRS 4  // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
+#define FA_EMU_PAIRS 2        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
+#endif
+#ifndef FA_EMU_PAIRS_LAST
+#define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
+#endif
+#ifndef FA_SPLIT_P
+#define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
+#endif
+#ifndef FA_REGS_SOFTMAX
+#define FA_REGS_SOFTMAX 208   // setmaxnreg for the softmax warpgroups ...
+#endif
+#ifndef FA_REGS_CTRL
+#define FA_REGS_CTRL 88       // ... and the control warpgroup (2*128*S + 128*C <= 384*168)
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
-// evenly spread `n` emulated pairs over the 16 pairs of a 32-column fragment
+constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
+constexpr bool kSplitP = FA_SPLIT_P != 0;
+static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
+// evenly spread `n` emulated pairs over the 16 pairs of a fragment
 __host__ __device__ constexpr bool emulate_pair(int pair, int n) {
     return n > 0 && ((pair * n) % 16) < n;
 }
 
-// Lazy rescale threshold in log2 units: O_g and l_g are only rescaled when the running max grows
-// by more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in
-// fp32, representable in bf16/fp16).  The final normalisation is unaffected.
+// Lazy rescale threshold in log2 units: O and l are only rescaled when the running max grows by
+// more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in fp32,
+// representable in bf16/fp16).  The final O/l is unaffected.
 constexpr float kRescaleThreshold = 8.0f;
 
 // Bring-up hooks (only read by the kDebug instantiation; see tools/gpu_bringup.py).
 struct FwdDebug {
-    float* dump;      // level 2: raw smem Q | K0 (2 x 8192 words); level >= 3: S(block 0) [128][128],
-                      // then m_g [2][128], l_g [2][128] of CTA 0
-    uint32_t level;   // 1: setup/teardown only, 2: + TMA Q,K0, 3: + S = QK^T, >= 4: everything
+    float* dump;      // level 2: raw smem Q_0 | K_0 (2 x 8192 words); level >= 3: S(block 0)
+                      // [2][128][128] of work tile 0, then l [2][128], m [2][128]
+    uint32_t level;   // 1: setup/teardown only, 2: + TMA Q_0,K_0, 3: + S = QK^T, >= 4: everything
     uint32_t* diag;   // host-mapped diagnostics ring (hang-guard builds)
 };
 
@@ -84,7 +98,8 @@ struct FwdParams {
     int seq_len;
     int n_heads;
     int n_kv_blocks;   // seq_len / 128
-    int n_q_tiles;     // seq_len / 128: CTAs per (batch, head)
+    int n_q_pairs;     // ceil(seq_len / 256): work tiles per (batch, head)
+    int n_tiles;       // batch * n_heads * n_q_pairs
     float scale_log2;  // log2(e) / sqrt(d_head)
 };
 
@@ -103,23 +118,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
     // barrier addresses
     const uint32_t bar0 = smem_base + kSmemBar;
-    const uint32_t q_full = bar0;
-    auto kv_full = [&](int i) { return bar0 + 8u * (1 + i); };
-    auto kv_empty = [&](int i) { return bar0 + 8u * (1 + kKVStages + i); };
-    auto s_full = [&](int x) { return bar0 + 8u * (1 + 2 * kKVStages + x); };
-    auto p_full = [&](int x, int g) { return bar0 + 8u * (3 + 2 * kKVStages + 2 * x + g); };
-    auto pv_done = [&](int g) { return bar0 + 8u * (7 + 2 * kKVStages + g); };
+    auto q_full = [&](int s) { return bar0 + 8u * s; };
+    auto q_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto kv_full = [&](int i) { return bar0 + 8u * (4 + i); };
+    auto kv_empty = [&](int i) { return bar0 + 8u * (4 + kKVStages + i); };
+    auto s_full = [&](int s) { return bar0 + 8u * (4 + 2 * kKVStages + s); };
+    auto p_full = [&](int s) { return bar0 + 8u * (6 + 2 * kKVStages + s); };
+    auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kKVStages + s); };
+    auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kKVStages + s); };
+    auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kKVStages + s); };
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
 
-    // tile coordinates: q tile fastest so co-resident CTAs share K/V of one (b, h) in L2
-    const int tile = blockIdx.x;
-    const int qtile = tile % prm.n_q_tiles;
-    const int bh = tile / prm.n_q_tiles;
-    const int head = bh % prm.n_heads;
-    const int batch = bh / prm.n_heads;
     const int n_blocks = prm.n_kv_blocks;
-
     const uint32_t level = kDebug ? dbg.level : 4u;
+    // work tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (q-pair index fastest so
+    // the CTAs running at the same time share the K/V of a few (batch, head) pairs in L2)
+    const int tile_end = (kDebug && level < 4) ? min(prm.n_tiles, (int)blockIdx.x + 1) : prm.n_tiles;
+    struct TileCoord {
+        int q_row0, head, batch;
+    };
+    auto coord_of = [&](int tile) {
+        TileCoord tc;
+        const int qpair = tile % prm.n_q_pairs;
+        const int bh = tile / prm.n_q_pairs;
+        tc.q_row0 = qpair * (kQStages * kBlockM);
+        tc.head = bh % prm.n_heads;
+        tc.batch = bh / prm.n_heads;
+        return tc;
+    };
+
 #if FA_HANG_GUARD
     if constexpr (kDebug) {
         if (threadIdx.x == 0) g_fa_diag = dbg.diag;
@@ -127,16 +154,18 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #endif
     if (warp == 8) {
         if (lane == 0) {
-            mbar_init(q_full, 1);
+            for (int s = 0; s < kQStages; ++s) {
+                mbar_init(q_full(s), 1);
+                mbar_init(q_empty(s), 1);
+                mbar_init(s_full(s), 1);
+                mbar_init(p_full(s), 4);  // one elected arrive per softmax warp
+                mbar_init(p_last(s), 4);
+                mbar_init(o_full(s), 1);
+                mbar_init(o_free(s), 4);
+            }
             for (int i = 0; i < kKVStages; ++i) {
                 mbar_init(kv_full(i), 1);
                 mbar_init(kv_empty(i), 1);
-            }
-            for (int x = 0; x < 2; ++x) {
-                mbar_init(s_full(x), 1);
-                mbar_init(pv_done(x), 1);
-                mbar_init(p_full(x, 0), 4);  // one elected arrive per softmax warp
-                mbar_init(p_full(x, 1), 4);
             }
             fence_mbar_init();
         }
@@ -153,36 +182,46 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr);
-    const uint32_t tmem_s0 = tmem_base;                  // S[x] at + x * 128
-    const uint32_t tmem_o0 = tmem_base + 2 * kBlockN;    // O_g at + g * 128
 
     if (wg == 2) {
+        setmaxnreg_dec<FA_REGS_CTRL>();
         if (warp == 9) {
             // ================================ TMA producer ================================
             if (lane == 0) {
-                auto load_tile = [&](const CUtensorMap* map, uint32_t dst, uint32_t bar, int row0) {
-                    mbar_arrive_expect_tx(bar, kTileBytes);
-                    tma_load_4d(dst, map, bar, 0, head, row0, batch);
-                    tma_load_4d(dst + kHalfBytes, map, bar, 64, head, row0, batch);
-                };
-                int item = 0;  // ring order: K0, K1, V0, K2, V1, K3, ... (the MMA warp's order)
-                auto load_kv = [&](const CUtensorMap* map, int blk) {
-                    const int slot = item % kKVStages;
-                    const uint32_t use = item / kKVStages;
-                    mbar_wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
-                    load_tile(map, smem_base + kSmemKV + slot * kTileBytes, kv_full(slot),
-                              blk * kBlockN);
-                    ++item;
-                };
-                if (level >= 2) {
-                    load_tile(&tm_q, smem_base + kSmemQ, q_full, qtile * kBlockM);
-                    load_kv(&tm_k, 0);
-                }
-                if (level >= 4) {
-                    if (n_blocks > 1) load_kv(&tm_k, 1);
-                    for (int j = 0; j < n_blocks; ++j) {
-                        load_kv(&tm_v, j);
-                        if (j + 2 < n_blocks) load_kv(&tm_k, j + 2);
+                int item = 0;  // K/V ring item counter (runs across tiles): K0, V0, K1, V1, ...
+                int it = 0;    // local tile counter
+                for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+                    const TileCoord tc = coord_of(tile);
+                    auto load_tile = [&](const CUtensorMap* map, uint32_t dst, uint32_t bar, int row0) {
+                        mbar_arrive_expect_tx(bar, kTileBytes);
+                        tma_load_4d(dst, map, bar, 0, tc.head, row0, tc.batch);
+                        tma_load_4d(dst + kHalfBytes, map, bar, 64, tc.head, row0, tc.batch);
+                    };
+                    auto load_q = [&](int s) {
+                        // Q_s smem is free once the previous tile's last S_s MMA retired
+                        mbar_wait(q_empty(s), (uint32_t)((it & 1) ^ 1), 110 + s);
+                        load_tile(&tm_q, smem_base + kSmemQ + s * kTileBytes, q_full(s),
+                                  tc.q_row0 + s * kBlockM);
+                    };
+                    auto load_kv = [&](const CUtensorMap* map, int blk) {
+                        const int slot = item % kKVStages;
+                        const uint32_t use = item / kKVStages;
+                        mbar_wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
+                        load_tile(map, smem_base + kSmemKV + slot * kTileBytes, kv_full(slot),
+                                  blk * kBlockN);
+                        ++item;
+                    };
+                    if (level >= 2) {
+                        load_q(0);
+                        load_kv(&tm_k, 0);
+                    }
+                    if (level >= 3) load_q(1);
+                    if (level >= 4) {
+                        load_kv(&tm_v, 0);
+                        for (int j = 1; j < n_blocks; ++j) {
+                            load_kv(&tm_k, j);
+                            load_kv(&tm_v, j);
+                        }
                     }
                 }
             }
@@ -193,38 +232,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kBlockM, kHeadDim, true);
                 // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
                 // V tiles: MN-major; next 64-wide d chunk 16 KiB away (LBO), next 8 kv rows 1 KiB
-                // (SBO); one k-step = 16 kv rows = 2 KiB.
-                const uint64_t q_desc = umma_smem_desc_sw128(smem_base + kSmemQ, 16, 1024);
-                auto issue_qk = [&](int x, int slot) {
+                // (SBO); one k-step = 16 kv rows = 2 KiB.  P (A operand in TMEM): 8 columns/k-step.
+                auto issue_qk = [&](int s, int slot) {
+                    const uint64_t a0 =
+                        umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, 16, 1024);
                     const uint64_t b0 =
                         umma_smem_desc_sw128(smem_base + kSmemKV + slot * kTileBytes, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < kHeadDim / 16; ++k) {
                         const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
-                        umma_ss(tmem_s0 + x * kBlockN, q_desc + off, b0 + off, idesc_qk, k > 0);
+                        umma_ss(tmem_base + s * kBlockN, a0 + off, b0 + off, idesc_qk, k > 0);
                     }
                 };
-                auto issue_pv = [&](int g, int x, int slot, bool accumulate) {
+                auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
                     const uint64_t b0 = umma_smem_desc_sw128(
-                        smem_base + kSmemKV + slot * kTileBytes + g * (kKeysPerWG / 16) * 2048,
-                        kHalfBytes, 1024);
+                        smem_base + kSmemKV + slot * kTileBytes, kHalfBytes, 1024);
 #pragma unroll
-                    for (int k = 0; k < kKeysPerWG / 16; ++k) {
-                        umma_ts(tmem_o0 + g * kHeadDim,
-                                tmem_s0 + x * kBlockN + g * kKeysPerWG + k * 8,
-                                b0 + ((k * 2048) >> 4), idesc_pv, (accumulate || k > 0) ? 1u : 0u);
+                    for (int k = k_begin; k < k_end; ++k) {
+                        umma_ts(tmem_base + 2 * kBlockN + s * kHeadDim,
+                                tmem_base + s * kBlockN + k * 8, b0 + ((k * 2048) >> 4), idesc_pv,
+                                (accumulate || k > 0) ? 1u : 0u);
                     }
                 };
-                int item = 0;
-                auto slot_of = [&](int it) { return it % kKVStages; };
-                auto wait_item = [&](int it, int tag) {
-                    mbar_wait(kv_full(slot_of(it)), (uint32_t)((it / kKVStages) & 1), tag);
-                    tc_fence_after();
-                };
+                auto slot_of = [&](int i) { return i % kKVStages; };
+                auto parity_of = [&](int i) { return (uint32_t)((i / kKVStages) & 1); };
+
                 if constexpr (kDebug) {
-                    if (level == 2) {  // raw smem images of Q and K0 as TMA wrote them
+                    if (level == 2) {  // raw smem images of Q_0 and K_0 as TMA wrote them
                         mbar_wait(kv_full(0), 0, 200);
-                        mbar_wait(q_full, 0, 210);
+                        mbar_wait(q_full(0), 0, 210);
                         if (dbg.dump != nullptr && blockIdx.x == 0) {
                             const uint32_t* qs = reinterpret_cast<const uint32_t*>(smem_gen + kSmemQ);
                             const uint32_t* ks = reinterpret_cast<const uint32_t*>(smem_gen + kSmemKV);
@@ -234,38 +270,55 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         }
                     }
                 }
-                if (level >= 3) {
-                    // prologue: S[0] = Q K_0^T, S[1] = Q K_1^T
-                    mbar_wait(q_full, 0, 210);
-                    const int n_pro = (level >= 4 && n_blocks > 1) ? 2 : 1;
-                    for (int x = 0; x < n_pro; ++x) {
-                        wait_item(item, 200 + x);
-                        issue_qk(x, slot_of(item));
-                        umma_commit(s_full(x));
-                        umma_commit(kv_empty(slot_of(item)));
-                        ++item;
-                    }
-                }
-                for (int j = 0; level >= 4 && j < n_blocks; ++j) {
-                    const int x = j & 1;
-                    const uint32_t par = (uint32_t)((j >> 1) & 1);
-                    const int it_v = item++;
-                    wait_item(it_v, 220);
-#pragma unroll
-                    for (int g = 0; g < kKeySplit; ++g) {
-                        mbar_wait(p_full(x, g), par, 230 + g);  // P_g(j) stored, O_g rescaled
+                int item = 0;    // K/V ring item counter, same order as the producer
+                uint32_t g = 0;  // KV blocks processed so far (all tiles): parity of s/p barriers
+                int it = 0;
+                for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
+                    // prologue: S_s(0) = Q_s K_0^T.  S_s is free: the PV that consumed the previous
+                    // tile's last P_s was issued before (in-order tensor pipe).
+                    mbar_wait(kv_full(slot_of(item)), parity_of(item), 200);
+                    for (int s = 0; s < kQStages; ++s) {
+                        mbar_wait(q_full(s), (uint32_t)(it & 1), 210 + s);
                         tc_fence_after();
-                        issue_pv(g, x, slot_of(it_v), j > 0);
-                        umma_commit(pv_done(g));
+                        issue_qk(s, slot_of(item));
+                        umma_commit(s_full(s));
+                        if (n_blocks == 1) umma_commit(q_empty(s));
                     }
-                    umma_commit(kv_empty(slot_of(it_v)));
-                    if (j + 2 < n_blocks) {
-                        // both P halves of S[x] are consumed (in-order tensor pipe): refill S[x]
-                        const int it_k = item++;
-                        wait_item(it_k, 240);
-                        issue_qk(x, slot_of(it_k));
-                        umma_commit(s_full(x));
-                        umma_commit(kv_empty(slot_of(it_k)));
+                    umma_commit(kv_empty(slot_of(item)));
+                    ++item;
+                    for (int j = 0; level >= 4 && j < n_blocks; ++j, ++g) {
+                        const int it_v = item;      // V_j
+                        const int it_k = item + 1;  // K_{j+1}
+                        const bool has_next = (j + 1 < n_blocks);
+                        mbar_wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
+                        for (int s = 0; s < kQStages; ++s) {
+                            mbar_wait(p_full(s), g & 1u, 230 + s);  // P_s(j) stored, O_s rescaled
+                            if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
+                                mbar_wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
+                            tc_fence_after();
+                            if constexpr (kSplitP) {
+                                issue_pv(s, slot_of(it_v), j > 0, 0, 6);
+                                mbar_wait(p_last(s), g & 1u, 250 + s);  // last 32 columns of P_s(j)
+                                tc_fence_after();
+                                issue_pv(s, slot_of(it_v), true, 6, 8);
+                            } else {
+                                issue_pv(s, slot_of(it_v), j > 0, 0, 8);
+                            }
+                            if (has_next) {
+                                if (s == 0) {
+                                    mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
+                                    tc_fence_after();
+                                }
+                                issue_qk(s, slot_of(it_k));
+                                umma_commit(s_full(s));
+                                if (j + 2 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
+                            } else {
+                                umma_commit(o_full(s));
+                            }
+                        }
+                        umma_commit(kv_empty(slot_of(it_v)));
+                        if (has_next) umma_commit(kv_empty(slot_of(it_k)));
+                        item += has_next ? 2 : 1;
                     }
                 }
             }
@@ -273,165 +326,172 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
     } else {
         // ==================================== softmax =====================================
-        const int g = wg;                    // key half owned by this warpgroup
-        const int row = threadIdx.x & 127;   // query row == TMEM lane
+        setmaxnreg_inc<FA_REGS_SOFTMAX>();
+        const int s = wg;                    // Q tile handled by this warpgroup
+        const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_s0 + lane_sel + g * kKeysPerWG;  // + x * 128
-        const uint32_t t_o = tmem_o0 + lane_sel + g * kHeadDim;    // own accumulator O_g
+        const uint32_t t_s = tmem_base + lane_sel + s * kBlockN;
+        const uint32_t t_p = t_s;
+        const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim;
         const float c = prm.scale_log2;
+        uint32_t g = 0;  // KV blocks processed so far (all tiles)
+        int it = 0;
 
-        float m_run = -INFINITY;  // running (possibly stale) max over this warpgroup's keys
-        float l_run = 0.f;        // running row sum of exp2 over this warpgroup's keys
-
-        const int n_iter = (level >= 4) ? n_blocks : (level == 3 ? 1 : 0);
-        for (int j = 0; j < n_iter; ++j) {
-            const int x = j & 1;
-            mbar_wait(s_full(x), (uint32_t)((j >> 1) & 1), 300 + g);
-            tc_fence_after();
-            uint32_t sr[2][32];
-            tmem_ld_32x32b_x32(t_s + x * kBlockN, sr[0]);
-            tmem_ld_32x32b_x32(t_s + x * kBlockN + 32, sr[1]);
-            tmem_wait_ld();
-
-            if constexpr (kDebug) {
-                if (dbg.dump != nullptr && blockIdx.x == 0 && j == 0) {
-                    for (int q = 0; q < 2; ++q)
-                        for (int i = 0; i < 32; ++i)
-                            dbg.dump[row * 128 + g * kKeysPerWG + q * 32 + i] =
-                                __uint_as_float(sr[q][i]);
-                }
-                if (level == 3) break;
-            }
-            // row max: 4 independent chains
-            float mxs[4];
+        for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
+            float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
+            float l_run = 0.f;        // running row sum of exp2
+            const int n_iter = (level >= 4) ? n_blocks : 1;
+            for (int j = 0; j < n_iter; ++j, ++g) {
+                mbar_wait(s_full(s), g & 1u, 300 + s);
+                tc_fence_after();
+                uint32_t sr[4][32];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                for (int i = 1; i < 16; ++i) {
-                    mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
-                    mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
-                }
-            }
-            float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-            mx = fmaxf(mx, m_run);
-            float alpha = 1.f;
-            if (j == 0) {
-                m_run = mx;
-            } else {
-                const float delta = (mx - m_run) * c;  // >= 0
-                const bool need = delta > kRescaleThreshold;
-                if (__any_sync(0xffffffffu, need)) {
-                    if (need) {
-                        alpha = ex2_approx(-delta);
-                        m_run = mx;
-                    }
-                    // O_g must be quiescent: wait until PV_g(j-1) retired.
-                    mbar_wait(pv_done(g), (uint32_t)((j - 1) & 1), 320 + g);
-                    tc_fence_after();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t o[32];
-                        tmem_ld_32x32b_x32(t_o + q * 32, o);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32b_x32(t_o + q * 32, o);
-                    }
-                }
-            }
-            const float neg_mc = -m_run * c;
-            const float2 c2 = make_float2(c, c);
-            const float2 nm2 = make_float2(neg_mc, neg_mc);
-            float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 xv = __ffma2_rn(
-                        make_float2(__uint_as_float(sr[q][2 * i]), __uint_as_float(sr[q][2 * i + 1])),
-                        c2, nm2);
-                    float2 p;
-                    if (emulate_pair(i, kEmuPairs)) {
-                        p = ex2_emulated_x2(xv);
-                    } else {
-                        p.x = ex2_approx(xv.x);
-                        p.y = ex2_approx(xv.y);
-                    }
-                    if (i & 1) sum_a = __fadd2_rn(sum_a, p);
-                    else sum_b = __fadd2_rn(sum_b, p);
-                    pk[i] = pack_16x2<kBF16>(p.x, p.y);
-                }
-                // P_g(j): 16-bit pairs over the first 32 columns of this warpgroup's S half
-                tmem_st_32x32b_x16(t_s + x * kBlockN + q * 16, pk);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full(x, g));
-            l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
-        }
-
-        // --------------------------------- epilogue --------------------------------------
-        if (level >= 4) {
-            // every MMA retired => both accumulators final, all smem tiles dead
-            mbar_wait(pv_done(0), (uint32_t)((n_blocks - 1) & 1), 310);
-            mbar_wait(pv_done(1), (uint32_t)((n_blocks - 1) & 1), 311);
-            tc_fence_after();
-            // exchange (m_g, l_g) through the (dead) first K/V slot
-            float2* stats = reinterpret_cast<float2*>(smem_gen + kSmemKV);
-            stats[g * kBlockM + row] = make_float2(m_run, l_run);
-            if constexpr (kDebug) {
-                if (dbg.dump != nullptr && blockIdx.x == 0) {
-                    dbg.dump[128 * 128 + g * 128 + row] = m_run;
-                    dbg.dump[128 * 128 + 256 + g * 128 + row] = l_run;
-                }
-            }
-            named_bar_sync(1, 2 * 128);
-            const float2 st0 = stats[row];
-            const float2 st1 = stats[kBlockM + row];
-            const float m_all = fmaxf(st0.x, st1.x);
-            const float a0 = ex2_approx((st0.x - m_all) * c);
-            const float a1 = ex2_approx((st1.x - m_all) * c);
-            const float inv = 1.0f / (a0 * st0.y + a1 * st1.y);
-            const float w0 = a0 * inv, w1 = a1 * inv;
-            // warpgroup g produces d columns [64g, 64g+64) == TMA box g, staged in the (dead) Q
-            // tile with the 128B swizzle: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)).
-            uint8_t* stage = smem_gen + kSmemQ + g * kHalfBytes + row * 128;
-            const uint32_t t_o0 = tmem_o0 + lane_sel + g * 64;
-            const uint32_t t_o1 = t_o0 + kHeadDim;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint32_t o0[32], o1[32];
-                tmem_ld_32x32b_x32(t_o0 + q * 32, o0);
-                tmem_ld_32x32b_x32(t_o1 + q * 32, o1);
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
                 tmem_wait_ld();
-#pragma unroll
-                for (int cidx = 0; cidx < 4; ++cidx) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        f[e] = fmaf(w1, __uint_as_float(o1[cidx * 8 + e]),
-                                    w0 * __uint_as_float(o0[cidx * 8 + e]));
-                    uint4 v;
-                    v.x = pack_16x2<kBF16>(f[0], f[1]);
-                    v.y = pack_16x2<kBF16>(f[2], f[3]);
-                    v.z = pack_16x2<kBF16>(f[4], f[5]);
-                    v.w = pack_16x2<kBF16>(f[6], f[7]);
-                    const int chunk = (q * 4 + cidx) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(stage + chunk * 16) = v;
+
+                if constexpr (kDebug) {
+                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j == 0) {
+                        for (int q = 0; q < 4; ++q)
+                            for (int i = 0; i < 32; ++i)
+                                dbg.dump[(s * 128 + row) * 128 + q * 32 + i] =
+                                    __uint_as_float(sr[q][i]);
+                    }
+                    if (level == 3) break;
                 }
+                // row max: 8 independent chains (a serial chain would cost 43 x 4+ cycles of latency)
+                float mxs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int i = 1; i < 16; ++i) {
+                        mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
+                        mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
+                    }
+                }
+                float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                 fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+                mx = fmaxf(mx, m_run);
+                float alpha = 1.f;
+                if (j == 0) {
+                    m_run = mx;
+                } else {
+                    const float delta = (mx - m_run) * c;  // >= 0
+                    const bool need = delta > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) {
+                            alpha = ex2_approx(-delta);
+                            m_run = mx;
+                        }
+                        // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t o[32];
+                            tmem_ld_32x32b_x32(t_o + q * 32, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32b_x32(t_o + q * 32, o);
+                        }
+                    }
+                }
+                const float neg_mc = -m_run * c;
+                const float2 c2 = make_float2(c, c);
+                const float2 nm2 = make_float2(neg_mc, neg_mc);
+                float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 x = __ffma2_rn(
+                            make_float2(__uint_as_float(sr[q][2 * i]),
+                                        __uint_as_float(sr[q][2 * i + 1])),
+                            c2, nm2);
+                        float2 p;
+                        if (emulate_pair(i, q == 3 ? kEmuPairsLast : kEmuPairs)) {
+                            p = ex2_emulated_x2(x);
+                        } else {
+                            p.x = ex2_approx(x.x);
+                            p.y = ex2_approx(x.y);
+                        }
+                        if (i & 1) sum_a = __fadd2_rn(sum_a, p);
+                        else sum_b = __fadd2_rn(sum_b, p);
+                        pk[i] = pack_16x2<kBF16>(p.x, p.y);
+                    }
+                    tmem_st_32x32b_x16(t_p + q * 16, pk);
+                    if (kSplitP && q == 2) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(p_full(s));
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
+                l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
             }
-            fence_proxy_async_smem();
-            named_bar_sync(2 + g, 128);
-            if (row == 0) {
-                tma_store_4d(&tm_o, smem_base + kSmemQ + g * kHalfBytes, 64 * g, head,
-                             qtile * kBlockM, batch);
-                tma_store_commit();
-                tma_store_wait_read<0>();
+
+            // ------------------------------- epilogue ------------------------------------
+            if (level >= 4) {
+                mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
+                tc_fence_after();
+                const float inv_l = 1.0f / l_run;
+                if constexpr (kDebug) {
+                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0) {
+                        dbg.dump[2 * 128 * 128 + s * 128 + row] = l_run;
+                        dbg.dump[2 * 128 * 128 + 256 + s * 128 + row] = m_run;
+                    }
+                }
+                // O_s -> registers (all 128 columns), then hand the accumulator back to the MMA
+                // warp so the next tile's first PV_s can proceed while we convert and store.
+                uint32_t o[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_o + q * 32, o[q]);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_free(s));
+                // Two passes of 64 columns (= one TMA box) through this warpgroup's 16 KiB staging
+                // buffer, written with the TMA 128B swizzle: 16-byte chunk c of row r lives at
+                // chunk (c ^ (r & 7)) of that row.
+                const TileCoord tc = coord_of(tile);
+                uint8_t* stage_row = smem_gen + kSmemStage + s * kHalfBytes + row * 128;
+                const uint32_t stage_u32 = smem_base + kSmemStage + s * kHalfBytes;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int q = 2 * h + qq;
+#pragma unroll
+                        for (int cidx = 0; cidx < 4; ++cidx) {
+                            uint4 v;
+                            v.x = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 0]) * inv_l,
+                                                   __uint_as_float(o[q][cidx * 8 + 1]) * inv_l);
+                            v.y = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 2]) * inv_l,
+                                                   __uint_as_float(o[q][cidx * 8 + 3]) * inv_l);
+                            v.z = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 4]) * inv_l,
+                                                   __uint_as_float(o[q][cidx * 8 + 5]) * inv_l);
+                            v.w = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 6]) * inv_l,
+                                                   __uint_as_float(o[q][cidx * 8 + 7]) * inv_l);
+                            const int chunk = (qq * 4 + cidx) ^ (row & 7);
+                            *reinterpret_cast<uint4*>(stage_row + chunk * 16) = v;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + s, 128);
+                    if (row == 0) {
+                        tma_store_4d(&tm_o, stage_u32, 64 * h, tc.head, tc.q_row0 + s * kBlockM,
+                                     tc.batch);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();  // staging buffer reusable
+                    }
+                    named_bar_sync(1 + s, 128);
+                }
             }
         }
     }

@@ -73,7 +73,7 @@ const char* fa_last_error_string(void);
 int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_capability);
 
 /* Static facts about the built kernel: dynamic shared memory per CTA, threads per CTA,
- * query rows per CTA, TMEM columns. */
+ * query rows per work tile (the kernel is persistent: one CTA per SM walks the tiles), TMEM columns. */
 int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_cols);
 
 /* Number of kernel launches issued through this library since load (all threads). */

@@ -43,7 +43,7 @@ def test_kernel_info(lib):
     from flash_attention_from_scratch_b200 import _lib
 
     info = _lib.kernel_info()
-    assert info["rows_per_cta"] == 128 and info["tmem_cols"] == 512
+    assert info["rows_per_cta"] == 256 and info["tmem_cols"] == 512
     assert info["smem_bytes"] <= 227 * 1024
     assert _lib.launch_count() == 0 or torch.cuda.is_available()
 

@@ -52,7 +52,9 @@ def test_golden_fixtures(golden):
 
 # ------------------------------------------------------------------ seeded shapes, both dtypes
 SHAPES = [(1, 128, 2), (1, 256, 1), (2, 384, 3), (2, 512, 16), (1, 1024, 32), (3, 640, 5),
-          (1, 2048, 4), (2, 1152, 7)]
+          (1, 2048, 4), (2, 1152, 7),
+          # more work tiles than SMs (persistent CTAs walk several tiles), odd / single block counts
+          (8, 384, 40), (16, 128, 33), (3, 1280, 37)]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
