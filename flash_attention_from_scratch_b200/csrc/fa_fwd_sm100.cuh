@@ -57,7 +57,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 
 // Tunables (overridable with -D at build time; tools/build_variants.py sweeps them).
 #ifndef FA_EMU_PAIRS
-#define FA_EMU_PAIRS 2        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
+#define FA_EMU_PAIRS 0        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
 #endif
 #ifndef FA_EMU_PAIRS_LAST
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
