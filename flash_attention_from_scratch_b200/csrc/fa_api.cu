@@ -200,10 +200,6 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     const long long n_tiles = 1LL * p.B * p.H * prm.n_q_pairs;
     if (n_tiles > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld tiles", n_tiles);
     prm.n_tiles = static_cast<int>(n_tiles);
-    prm.o_ptr = p.o;
-    prm.o_stride_b = p.sb;
-    prm.o_stride_n = p.sn;
-    prm.o_stride_h = p.sh;
     // persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
     dim3 grid((unsigned)(n_tiles < n_sms ? n_tiles : n_sms)), block(fa::kNumThreads);

@@ -17,20 +17,14 @@
 //   * one thread issues tcgen05.mma: S_s = Q_s K_j^T (operands from smem) and O_s += P_s V_j
 //     (P read from tensor memory, V from smem, MN-major); accumulators in TMEM:
 //       columns [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1
-//   * FOUR softmax warpgroups, two per Q tile: warpgroup (s, h) owns key columns [64h, 64h+64) of
-//     S_s, one thread per (row, half).  tcgen05.ld S, partial row max, the two halves of a row
-//     exchange their partial max through shared memory (one 64-thread named barrier per warp
-//     pair), fp32 exp2 / partial row sum in registers, P written back to TMEM as packed 16-bit
-//     over the first 32 columns of the thread's OWN S half (so PV of half 0 can start before half 1
-//     is done), lazy rescale of O (only when the row max grew by more than 2^8).  Four warps per
-//     SM sub-partition instead of two: generations 2-4 were bound by the latency of the softmax
-//     phase (profiles/r01_v2_ncu_notes.md), halving the per-thread serial work shortens it.
-//   * epilogue: partial row sums are exchanged the same way, O_s * (1/l) is rounded to 16 bit and
-//     stored straight from registers (each thread owns 128 contiguous bytes of one output row).
+//   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
+//     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit in two
+//     parts (96 + 32 columns) so PV starts early, lazy rescale of O (only when the row max grew
+//     by more than 2^8), final 1/l scaling and TMA store of O through swizzled shared memory.
 //   The two Q tiles ping-pong: while the tensor core runs PV_1(j-1) and S_1(j) the softmax
-//   warpgroups of tile 0 work on S_0(j), and vice versa.
+//   warpgroup 0 works on S_0(j), and vice versa.
 //
-// Generations 1-4 and the measurements that led here: profiles/r01_*_notes.md.
+// Generations 1-3 and the measurements that led here: profiles/r01_*_notes.md.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -48,15 +42,13 @@ constexpr int kQStages = 2;    // Q tiles per work tile
 constexpr int kKVStages = 4;   // K/V ring slots (each slot holds one K block or one V block)
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
-constexpr int kNumThreads = 640;                    // 4 softmax warpgroups + 1 control warpgroup
-constexpr int kSoftmaxWarps = 16;                   // warps 0..15; warp 16 = MMA, 17 = TMA
+constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
 constexpr int kTmemCols = 512;
 
 constexpr int kSmemQ = 0;                                       // Q_0, Q_1
 constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;         // K/V ring
-constexpr int kSmemXchg = kSmemKV + kKVStages * kTileBytes;     // row max / row sum exchange
-constexpr int kXchgBytes = 2 * kQStages * 2 * kBlockM * 4;     // [max|sum][stage][half][row] fp32
-constexpr int kSmemBar = kSmemXchg + kXchgBytes;
+constexpr int kSmemStage = kSmemKV + kKVStages * kTileBytes;    // O staging: 16 KiB per Q tile
+constexpr int kSmemBar = kSmemStage + kQStages * kHalfBytes;
 constexpr int kNumBarriers = 4 + 2 * kKVStages + 10;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
@@ -70,15 +62,19 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #ifndef FA_EMU_PAIRS_LAST
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
 #endif
+#ifndef FA_SPLIT_P
+#define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
+#endif
 #ifndef FA_REGS_SOFTMAX
-#define FA_REGS_SOFTMAX 96    // setmaxnreg for the softmax warpgroups ...
+#define FA_REGS_SOFTMAX 208   // setmaxnreg for the softmax warpgroups ...
 #endif
 #ifndef FA_REGS_CTRL
-#define FA_REGS_CTRL 96       // ... and the control warpgroup (4*128*S + 128*C <= 640*96)
+#define FA_REGS_CTRL 88       // ... and the control warpgroup (2*128*S + 128*C <= 384*168)
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
-static_assert(512 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 640 * 96, "register pool exceeded");
+constexpr bool kSplitP = FA_SPLIT_P != 0;
+static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
 // evenly spread `n` emulated pairs over the 16 pairs of a fragment
 __host__ __device__ constexpr bool emulate_pair(int pair, int n) {
     return n > 0 && ((pair * n) % 16) < n;
@@ -93,9 +89,18 @@ constexpr float kRescaleThreshold = 8.0f;
 struct FwdDebug {
     float* dump;      // level 2: raw smem Q_0 | K_0 (2 x 8192 words); level >= 3: S(block 0)
                       // [2][128][128] of work tile 0, then l [2][128], m [2][128]
-    uint32_t level;   // 1: setup/teardown only, 2: + TMA Q_0,K_0, 3: + S = QK^T, >= 4: everything
+    uint32_t level;   // 1: setup/teardown only, 2: + TMA Q_0,K_0, 3: + S = QK^T, >= 4: everything,
+                      // 5: everything + cycle trace of CTA 0 / tile 0 (words from kTraceBase on:
+                      // softmax [stage][block<32][8 events], then MMA [block<32][stage][4 events])
     uint32_t* diag;   // host-mapped diagnostics ring (hang-guard builds)
 };
+
+constexpr int kTraceBase = 2 * 128 * 128 + 512;  // word offset of the trace inside FwdDebug::dump
+__device__ __forceinline__ uint32_t clk32() {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    return c;
+}
 
 struct FwdParams {
     int batch;
@@ -105,8 +110,6 @@ struct FwdParams {
     int n_q_pairs;     // ceil(seq_len / 256): work tiles per (batch, head)
     int n_tiles;       // batch * n_heads * n_q_pairs
     float scale_log2;  // log2(e) / sqrt(d_head)
-    void* o_ptr;       // output tensor and its strides in elements (stored from registers)
-    long long o_stride_b, o_stride_n, o_stride_h;
 };
 
 template <bool kBF16, bool kDebug>
@@ -129,7 +132,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     auto kv_full = [&](int i) { return bar0 + 8u * (4 + i); };
     auto kv_empty = [&](int i) { return bar0 + 8u * (4 + kKVStages + i); };
     auto s_full = [&](int s) { return bar0 + 8u * (4 + 2 * kKVStages + s); };
-    auto p_half = [&](int s, int h) { return bar0 + 8u * (6 + 2 * kKVStages + 2 * s + h); };
+    auto p_full = [&](int s) { return bar0 + 8u * (6 + 2 * kKVStages + s); };
+    auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kKVStages + s); };
     auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kKVStages + s); };
     auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kKVStages + s); };
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
@@ -157,16 +161,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (threadIdx.x == 0) g_fa_diag = dbg.diag;
     }
 #endif
-    if (warp == kSoftmaxWarps) {
+    if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < kQStages; ++s) {
                 mbar_init(q_full(s), 1);
                 mbar_init(q_empty(s), 1);
                 mbar_init(s_full(s), 1);
-                mbar_init(p_half(s, 0), 4);  // one elected arrive per softmax warp
-                mbar_init(p_half(s, 1), 4);
+                mbar_init(p_full(s), 4);  // one elected arrive per softmax warp
+                mbar_init(p_last(s), 4);
                 mbar_init(o_full(s), 1);
-                mbar_init(o_free(s), 8);
+                mbar_init(o_free(s), 4);
             }
             for (int i = 0; i < kKVStages; ++i) {
                 mbar_init(kv_full(i), 1);
@@ -177,7 +181,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
         tmem_alloc(tmem_ptr_smem, kTmemCols);
         tmem_relinquish();
-    } else if (warp == kSoftmaxWarps + 1 && lane == 0) {
+    } else if (warp == 9 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
@@ -186,21 +190,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr);
+    // All 512 TMEM columns are allocated by the only CTA on this SM, so the base address is 0.
+    // Using the literal keeps every tcgen05 operand warp-uniform (no R2UR per MMA).
+    if (*reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr) != 0u) {
+        if (threadIdx.x == 0) printf("[fa] unexpected TMEM base address\n");
+        __trap();
+    }
+    constexpr uint32_t tmem_base = 0u;
 
-    if (wg == 4) {
-        if constexpr (FA_REGS_CTRL < 96) setmaxnreg_dec<FA_REGS_CTRL>();
-        if (warp == kSoftmaxWarps + 1) {
+    if (wg == 2) {
+        setmaxnreg_dec<FA_REGS_CTRL>();
+        if (warp == 9) {
             // ================================ TMA producer ================================
-            if (lane == 0) {
+            // Convergent warp, one elected lane issues the copies (same reason as the MMA warp).
+            {
                 int item = 0;  // K/V ring item counter (runs across tiles): K0, V0, K1, V1, ...
                 int it = 0;    // local tile counter
                 for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
                     const TileCoord tc = coord_of(tile);
                     auto load_tile = [&](const CUtensorMap* map, uint32_t dst, uint32_t bar, int row0) {
-                        mbar_arrive_expect_tx(bar, kTileBytes);
-                        tma_load_4d(dst, map, bar, 0, tc.head, row0, tc.batch);
-                        tma_load_4d(dst + kHalfBytes, map, bar, 64, tc.head, row0, tc.batch);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(bar, kTileBytes);
+                            tma_load_4d(dst, map, bar, 0, tc.head, row0, tc.batch);
+                            tma_load_4d(dst + kHalfBytes, map, bar, 64, tc.head, row0, tc.batch);
+                        }
+                        __syncwarp();
                     };
                     auto load_q = [&](int s) {
                         // Q_s smem is free once the previous tile's last S_s MMA retired
@@ -230,9 +244,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     }
                 }
             }
-        } else if (warp == kSoftmaxWarps) {
+        } else if (warp == 8) {
             // ================================ MMA issuer ==================================
-            if (lane == 0) {
+            // The whole warp runs this loop CONVERGENTLY (all lanes poll the barriers) and one
+            // elected lane issues the tcgen05 instructions.  Issuing from a `lane == 0` divergent
+            // branch made ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY serialisation loop with
+            // three R2URs: ~90 cycles per MMA, more than the 64 cycles the MMA takes to execute
+            // (profiles/r01_v4_trace_notes.md).
+            {
                 constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, kBlockM, kBlockN, false);
                 constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kBlockM, kHeadDim, true);
                 // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
@@ -255,8 +274,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
                     for (int k = k_begin; k < k_end; ++k) {
                         umma_ts(tmem_base + 2 * kBlockN + s * kHeadDim,
-                                tmem_base + s * kBlockN + (k >> 2) * 64 + (k & 3) * 8,
-                                b0 + ((k * 2048) >> 4), idesc_pv, (accumulate || k > 0) ? 1u : 0u);
+                                tmem_base + s * kBlockN + k * 8, b0 + ((k * 2048) >> 4), idesc_pv,
+                                (accumulate || k > 0) ? 1u : 0u);
                     }
                 };
                 auto slot_of = [&](int i) { return i % kKVStages; };
@@ -266,7 +285,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     if (level == 2) {  // raw smem images of Q_0 and K_0 as TMA wrote them
                         mbar_wait(kv_full(0), 0, 200);
                         mbar_wait(q_full(0), 0, 210);
-                        if (dbg.dump != nullptr && blockIdx.x == 0) {
+                        if (lane == 0 && dbg.dump != nullptr && blockIdx.x == 0) {
                             const uint32_t* qs = reinterpret_cast<const uint32_t*>(smem_gen + kSmemQ);
                             const uint32_t* ks = reinterpret_cast<const uint32_t*>(smem_gen + kSmemKV);
                             uint32_t* out = reinterpret_cast<uint32_t*>(dbg.dump);
@@ -285,11 +304,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     for (int s = 0; s < kQStages; ++s) {
                         mbar_wait(q_full(s), (uint32_t)(it & 1), 210 + s);
                         tc_fence_after();
-                        issue_qk(s, slot_of(item));
-                        umma_commit(s_full(s));
-                        if (n_blocks == 1) umma_commit(q_empty(s));
+                        if (elect_one()) {
+                            issue_qk(s, slot_of(item));
+                            umma_commit(s_full(s));
+                            if (n_blocks == 1) umma_commit(q_empty(s));
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(kv_empty(slot_of(item)));
+                    if (elect_one()) umma_commit(kv_empty(slot_of(item)));
+                    __syncwarp();
                     ++item;
                     for (int j = 0; level >= 4 && j < n_blocks; ++j, ++g) {
                         const int it_v = item;      // V_j
@@ -297,28 +320,72 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         const bool has_next = (j + 1 < n_blocks);
                         mbar_wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
                         for (int s = 0; s < kQStages; ++s) {
-                            mbar_wait(p_half(s, 0), g & 1u, 230 + s);  // keys 0..63 of P_s(j) stored
+                            uint32_t* tr = nullptr;
+                            if constexpr (kDebug) {
+                                if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
+                                    j < 32 && lane == 0)
+                                    tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 512 +
+                                         (j * 2 + s) * 4;
+                            }
+                            mbar_wait(p_full(s), g & 1u, 230 + s);  // P_s(j) stored, O_s rescaled
+                            if constexpr (kDebug) {
+                                if (tr) tr[0] = clk32();
+                            }
                             if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
                                 mbar_wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
                             tc_fence_after();
-                            issue_pv(s, slot_of(it_v), j > 0, 0, 4);
-                            mbar_wait(p_half(s, 1), g & 1u, 250 + s);  // keys 64..127
-                            tc_fence_after();
-                            issue_pv(s, slot_of(it_v), true, 4, 8);
-                            if (has_next) {
-                                if (s == 0) {
+                            if constexpr (kSplitP) {
+                                if (elect_one()) issue_pv(s, slot_of(it_v), j > 0, 0, 6);
+                                __syncwarp();
+                                if constexpr (kDebug) {
+                                    if (tr) tr[1] = clk32();
+                                }
+                                mbar_wait(p_last(s), g & 1u, 250 + s);  // last 32 columns of P_s(j)
+                                if constexpr (kDebug) {
+                                    if (tr) tr[2] = clk32();
+                                }
+                                tc_fence_after();
+                                if (has_next && s == 0) {
                                     mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
                                     tc_fence_after();
                                 }
-                                issue_qk(s, slot_of(it_k));
-                                umma_commit(s_full(s));
-                                if (j + 2 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
+                                if (elect_one()) {
+                                    issue_pv(s, slot_of(it_v), true, 6, 8);
+                                    if (has_next) {
+                                        issue_qk(s, slot_of(it_k));
+                                        umma_commit(s_full(s));
+                                        if (j + 2 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
+                                    } else {
+                                        umma_commit(o_full(s));
+                                    }
+                                }
+                                __syncwarp();
                             } else {
-                                umma_commit(o_full(s));
+                                if (has_next && s == 0) {
+                                    mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
+                                    tc_fence_after();
+                                }
+                                if (elect_one()) {
+                                    issue_pv(s, slot_of(it_v), j > 0, 0, 8);
+                                    if (has_next) {
+                                        issue_qk(s, slot_of(it_k));
+                                        umma_commit(s_full(s));
+                                        if (j + 2 == n_blocks) umma_commit(q_empty(s));
+                                    } else {
+                                        umma_commit(o_full(s));
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            if constexpr (kDebug) {
+                                if (tr) tr[3] = clk32();
                             }
                         }
-                        umma_commit(kv_empty(slot_of(it_v)));
-                        if (has_next) umma_commit(kv_empty(slot_of(it_k)));
+                        if (elect_one()) {
+                            umma_commit(kv_empty(slot_of(it_v)));
+                            if (has_next) umma_commit(kv_empty(slot_of(it_k)));
+                        }
+                        __syncwarp();
                         item += has_next ? 2 : 1;
                     }
                 }
@@ -327,85 +394,77 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         __syncwarp();
     } else {
         // ==================================== softmax =====================================
-        if constexpr (FA_REGS_SOFTMAX > 96) setmaxnreg_inc<FA_REGS_SOFTMAX>();
-        const int s = wg >> 1;               // Q tile handled by this warpgroup
-        const int h = wg & 1;                // key-column half [64h, 64h+64) of every S_s block
+        setmaxnreg_inc<FA_REGS_SOFTMAX>();
+        const int s = wg;                    // Q tile handled by this warpgroup
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_sel + s * kBlockN + h * 64;  // my S columns; P over
-                                                                           // the first 32 of them
-        const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim + h * 64;
+        const uint32_t t_s = tmem_base + lane_sel + s * kBlockN;
+        const uint32_t t_p = t_s;
+        const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim;
         const float c = prm.scale_log2;
-        // exchange slots: [0] partial row max, [1] partial row sum; indexed [stage][half][row]
-        float* xch = reinterpret_cast<float*>(smem_gen + kSmemXchg);
-        float* x_max_mine = xch + (s * 2 + h) * kBlockM + row;
-        float* x_max_other = xch + (s * 2 + (h ^ 1)) * kBlockM + row;
-        float* x_sum_mine = x_max_mine + kQStages * 2 * kBlockM;
-        float* x_sum_other = x_max_other + kQStages * 2 * kBlockM;
-        const uint32_t pair_bar = 1 + s * 4 + (warp & 3);  // my warp + the other half's warp
         uint32_t g = 0;  // KV blocks processed so far (all tiles)
         int it = 0;
 
         for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
-            float m_run = -INFINITY;  // running (possibly stale) row max, identical in both halves
-            float l_run = 0.f;        // running row sum of exp2 over MY 64 columns
+            float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
+            float l_run = 0.f;        // running row sum of exp2
             const int n_iter = (level >= 4) ? n_blocks : 1;
             for (int j = 0; j < n_iter; ++j, ++g) {
                 mbar_wait(s_full(s), g & 1u, 300 + s);
                 tc_fence_after();
-                // ---- pass 1: partial row max over my 64 columns (values are re-read in pass 2 to
-                //      keep the live register set small: 4 softmax warpgroups share the RF)
-                float mloc;
-                {
-                    uint32_t sr[2][32];
-                    tmem_ld_32x32b_x32(t_s, sr[0]);
-                    tmem_ld_32x32b_x32(t_s + 32, sr[1]);
-                    tmem_wait_ld();
-                    if constexpr (kDebug) {
-                        if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j == 0) {
-                            for (int q = 0; q < 2; ++q)
-                                for (int i = 0; i < 32; ++i)
-                                    dbg.dump[(s * 128 + row) * 128 + h * 64 + q * 32 + i] =
-                                        __uint_as_float(sr[q][i]);
-                        }
-                    }
-                    float mxs[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                        for (int i = 1; i < 16; ++i) {
-                            mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
-                            mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
-                        }
-                    }
-                    mloc = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-                }
+                uint32_t* tr = nullptr;
                 if constexpr (kDebug) {
+                    if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
+                        (warp & 3) == 0 && lane == 0)
+                        tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + (s * 32 + j) * 8;
+                    if (tr) tr[0] = clk32();
+                }
+                uint32_t sr[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+                tmem_wait_ld();
+                if constexpr (kDebug) {
+                    if (tr) tr[1] = clk32();
+                }
+
+                if constexpr (kDebug) {
+                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j == 0) {
+                        for (int q = 0; q < 4; ++q)
+                            for (int i = 0; i < 32; ++i)
+                                dbg.dump[(s * 128 + row) * 128 + q * 32 + i] =
+                                    __uint_as_float(sr[q][i]);
+                    }
                     if (level == 3) break;
                 }
-                // exchange with the thread that owns the other half of this row.  The slot is safe
-                // to overwrite: the partner read last block's value before it arrived on p_half,
-                // which precedes PV(j-1), which precedes S(j), which I just waited for.
-                *x_max_mine = mloc;
-                named_bar_sync(pair_bar, 64);
-                float mx = fmaxf(fmaxf(mloc, *x_max_other), m_run);
+                // row max: 8 independent chains (a serial chain would cost 43 x 4+ cycles of latency)
+                float mxs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int i = 1; i < 16; ++i) {
+                        mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
+                        mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
+                    }
+                }
+                float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                 fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+                mx = fmaxf(mx, m_run);
                 float alpha = 1.f;
                 if (j == 0) {
                     m_run = mx;
                 } else {
-                    const float delta = (mx - m_run) * c;  // >= 0, identical in both halves
+                    const float delta = (mx - m_run) * c;  // >= 0
                     const bool need = delta > kRescaleThreshold;
                     if (__any_sync(0xffffffffu, need)) {
                         if (need) {
                             alpha = ex2_approx(-delta);
                             m_run = mx;
                         }
-                        // O_s is quiescent here (S_s(j) was committed after PV_s(j-1)); each half
-                        // rescales its own 64 accumulator columns.
+                        // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
+                        for (int q = 0; q < 4; ++q) {
                             uint32_t o[32];
                             tmem_ld_32x32b_x32(t_o + q * 32, o);
                             tmem_wait_ld();
@@ -416,26 +475,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         }
                     }
                 }
-                // ---- pass 2: exp2, row sum, P.  Fragment q (32 S columns) is re-read, turned into
-                //      16 packed P columns and written over columns [16q, 16q+16) of MY S half,
-                //      which hold fragment 0 data that is no longer needed.
+                if constexpr (kDebug) {
+                    if (tr) tr[2] = clk32();
+                }
                 const float neg_mc = -m_run * c;
                 const float2 c2 = make_float2(c, c);
                 const float2 nm2 = make_float2(neg_mc, neg_mc);
                 float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    uint32_t sr[32];
-                    tmem_ld_32x32b_x32(t_s + q * 32, sr);
-                    tmem_wait_ld();
+                for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 x = __ffma2_rn(
-                            make_float2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])),
+                            make_float2(__uint_as_float(sr[q][2 * i]),
+                                        __uint_as_float(sr[q][2 * i + 1])),
                             c2, nm2);
                         float2 p;
-                        if (emulate_pair(i, q == 1 ? kEmuPairsLast : kEmuPairs)) {
+                        if (emulate_pair(i, q == 3 ? kEmuPairsLast : kEmuPairs)) {
                             p = ex2_emulated_x2(x);
                         } else {
                             p.x = ex2_approx(x.x);
@@ -445,48 +502,58 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         else sum_b = __fadd2_rn(sum_b, p);
                         pk[i] = pack_16x2<kBF16>(p.x, p.y);
                     }
-                    tmem_st_32x32b_x16(t_s + q * 16, pk);
+                    tmem_st_32x32b_x16(t_p + q * 16, pk);
+                    if (kSplitP && q == 2) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(p_full(s));
+                        if constexpr (kDebug) {
+                            if (tr) tr[3] = clk32();
+                        }
+                    }
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_half(s, h));
+                if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
+                if constexpr (kDebug) {
+                    if (tr) tr[4] = clk32();
+                }
                 l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
             }
 
             // ------------------------------- epilogue ------------------------------------
             if (level >= 4) {
-                // total row sum = my half + the other half
-                *x_sum_mine = l_run;
-                named_bar_sync(pair_bar, 64);
-                const float l_all = l_run + *x_sum_other;
-                const float inv_l = 1.0f / l_all;
+                mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
+                tc_fence_after();
+                const float inv_l = 1.0f / l_run;
                 if constexpr (kDebug) {
-                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && h == 0) {
-                        dbg.dump[2 * 128 * 128 + s * 128 + row] = l_all;
+                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0) {
+                        dbg.dump[2 * 128 * 128 + s * 128 + row] = l_run;
                         dbg.dump[2 * 128 * 128 + 256 + s * 128 + row] = m_run;
                     }
                 }
-                mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
-                tc_fence_after();
-                // my 64 columns of O_s -> registers, then hand the accumulator back to the MMA warp
-                // so the next tile's first PV_s can proceed while we convert and store.
-                uint32_t o[2][32];
-                tmem_ld_32x32b_x32(t_o, o[0]);
-                tmem_ld_32x32b_x32(t_o + 32, o[1]);
+                // O_s -> registers (all 128 columns), then hand the accumulator back to the MMA
+                // warp so the next tile's first PV_s can proceed while we convert and store.
+                uint32_t o[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_o + q * 32, o[q]);
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_free(s));
+                // Two passes of 64 columns (= one TMA box) through this warpgroup's 16 KiB staging
+                // buffer, written with the TMA 128B swizzle: 16-byte chunk c of row r lives at
+                // chunk (c ^ (r & 7)) of that row.
                 const TileCoord tc = coord_of(tile);
-                const int q_row = tc.q_row0 + s * kBlockM + row;
-                if (q_row < prm.seq_len) {  // (phantom second Q tile when seq_len % 256 == 128)
-                    uint4* dst = reinterpret_cast<uint4*>(
-                        reinterpret_cast<uint16_t*>(prm.o_ptr) + (long long)tc.batch * prm.o_stride_b +
-                        (long long)q_row * prm.o_stride_n + (long long)tc.head * prm.o_stride_h +
-                        h * 64);
+                uint8_t* stage_row = smem_gen + kSmemStage + s * kHalfBytes + row * 128;
+                const uint32_t stage_u32 = smem_base + kSmemStage + s * kHalfBytes;
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int q = 2 * h + qq;
 #pragma unroll
                         for (int cidx = 0; cidx < 4; ++cidx) {
                             uint4 v;
@@ -498,9 +565,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                                                    __uint_as_float(o[q][cidx * 8 + 5]) * inv_l);
                             v.w = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 6]) * inv_l,
                                                    __uint_as_float(o[q][cidx * 8 + 7]) * inv_l);
-                            dst[q * 4 + cidx] = v;
+                            const int chunk = (qq * 4 + cidx) ^ (row & 7);
+                            *reinterpret_cast<uint4*>(stage_row + chunk * 16) = v;
                         }
                     }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + s, 128);
+                    if (row == 0) {
+                        tma_store_4d(&tm_o, stage_u32, 64 * h, tc.head, tc.q_row0 + s * kBlockM,
+                                     tc.batch);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();  // staging buffer reusable
+                    }
+                    named_bar_sync(1 + s, 128);
                 }
             }
         }
@@ -509,7 +586,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     // ------------------------------------ teardown ---------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == kSoftmaxWarps) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }

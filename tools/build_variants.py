@@ -15,7 +15,8 @@ VARIANTS = {
     "emu0": {"FA_EMU_PAIRS": 0},
     "emu2": {"FA_EMU_PAIRS": 2},
     "emu4": {"FA_EMU_PAIRS": 4},
-    "emu6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "emu2_r200": {"FA_EMU_PAIRS": 2, "FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 104},
+    "emu2_r216": {"FA_EMU_PAIRS": 2, "FA_REGS_SOFTMAX": 216, "FA_REGS_CTRL": 72},
 }
 
 
