@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 
 #include "ptx_sm100.cuh"
+#include "softmax_sm100.cuh"
 
 namespace fa {
 
@@ -57,7 +58,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 
 // Tunables (overridable with -D at build time; tools/build_variants.py sweeps them).
 #ifndef FA_EMU_PAIRS
-#define FA_EMU_PAIRS 0        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
+#define FA_EMU_PAIRS 4        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
 #endif
 #ifndef FA_EMU_PAIRS_LAST
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
@@ -74,11 +75,15 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
 constexpr bool kSplitP = FA_SPLIT_P != 0;
+constexpr bool kPingPong = FA_PINGPONG != 0;
 static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
-// evenly spread `n` emulated pairs over the 16 pairs of a fragment
-__host__ __device__ constexpr bool emulate_pair(int pair, int n) {
-    return n > 0 && ((pair * n) % 16) < n;
-}
+#ifndef FA_PINGPONG
+#define FA_PINGPONG 1         // 1: the two softmax warpgroups take turns on the exp2 phase (token
+                              // passed through named barriers 3/4) instead of contending for MUFU
+#endif
+#ifndef FA_EXP_VARIANT
+#define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
+#endif
 
 // Lazy rescale threshold in log2 units: O and l are only rescaled when the running max grows by
 // more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in fp32,
@@ -404,6 +409,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const float c = prm.scale_log2;
         uint32_t g = 0;  // KV blocks processed so far (all tiles)
         int it = 0;
+        // exp2-phase token (softmax_probe: one warpgroup alone needs ~1400 cycles per block, two
+        // contending ones ~2100 each): warpgroup s waits on named barrier 3+s before its exp2
+        // phase and releases barrier 3+(1-s) after it.  Warpgroup 1 pre-arrives so 0 goes first.
+        if (kPingPong && level >= 4 && s == 1) named_bar_arrive(3, 256);
 
         for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
             float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
@@ -436,20 +445,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     }
                     if (level == 3) break;
                 }
-                // row max: 8 independent chains (a serial chain would cost 43 x 4+ cycles of latency)
-                float mxs[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) mxs[u] = __uint_as_float(sr[u >> 1][(u & 1) * 16]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int i = 1; i < 16; ++i) {
-                        mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[q][i]));
-                        mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[q][16 + i]));
-                    }
-                }
-                float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                                 fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+                float mx = row_max_128(sr);
                 mx = fmaxf(mx, m_run);
                 float alpha = 1.f;
                 if (j == 0) {
@@ -482,26 +478,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const float2 c2 = make_float2(c, c);
                 const float2 nm2 = make_float2(neg_mc, neg_mc);
                 float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+                if (kPingPong && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 x = __ffma2_rn(
-                            make_float2(__uint_as_float(sr[q][2 * i]),
-                                        __uint_as_float(sr[q][2 * i + 1])),
-                            c2, nm2);
-                        float2 p;
-                        if (emulate_pair(i, q == 3 ? kEmuPairsLast : kEmuPairs)) {
-                            p = ex2_emulated_x2(x);
-                        } else {
-                            p.x = ex2_approx(x.x);
-                            p.y = ex2_approx(x.y);
-                        }
-                        if (i & 1) sum_a = __fadd2_rn(sum_a, p);
-                        else sum_b = __fadd2_rn(sum_b, p);
-                        pk[i] = pack_16x2<kBF16>(p.x, p.y);
-                    }
+                    if (q == 3)
+                        exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    else
+                        exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     tmem_st_32x32b_x16(t_p + q * 16, pk);
                     if (kSplitP && q == 2) {
                         tmem_wait_st();
@@ -517,6 +501,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
+                if (kPingPong && level >= 4) named_bar_arrive(3 + (s ^ 1), 256);  // pass the token
                 if constexpr (kDebug) {
                     if (tr) tr[4] = clk32();
                 }
@@ -582,6 +567,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             }
         }
     }
+
+    // consume the last token hand-over so no named barrier is left half-arrived
+    if (kPingPong && level >= 4 && wg == 0 && (int)blockIdx.x < tile_end) named_bar_sync(3, 256);
 
     // ------------------------------------ teardown ---------------------------------------
     tc_fence_before();

@@ -12,11 +12,12 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "emu0": {"FA_EMU_PAIRS": 0},
-    "emu2": {"FA_EMU_PAIRS": 2},
-    "emu4": {"FA_EMU_PAIRS": 4},
-    "emu2_r200": {"FA_EMU_PAIRS": 2, "FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 104},
-    "emu2_r216": {"FA_EMU_PAIRS": 2, "FA_REGS_SOFTMAX": 216, "FA_REGS_CTRL": 72},
+    "pp_emu0": {"FA_EMU_PAIRS": 0},
+    "pp_emu4": {"FA_EMU_PAIRS": 4},
+    "pp_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
+    "pp_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "pp_emu8_8": {"FA_EMU_PAIRS": 8, "FA_EMU_PAIRS_LAST": 8},
+    "nopp_emu4": {"FA_EMU_PAIRS": 4, "FA_PINGPONG": 0},
 }
 
 

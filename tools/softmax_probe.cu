@@ -1,0 +1,182 @@
+// Timing probe for the softmax step of the attention kernel (development aid).
+//
+// Runs ONLY the per-block softmax work of one or two softmax warpgroups on every SM -- tcgen05.ld
+// of a 128-wide fp32 row, row max, exp2 / row sum / pack, tcgen05.st of P -- using the same device
+// functions as the production kernel (csrc/softmax_sm100.cuh), with the same register budget
+// (384 threads, setmaxnreg 208/88), and reports cycles per block and per sub-phase.  No MMA, no TMA:
+// this isolates the throughput of the softmax phase from the ping-pong with the tensor pipe.
+//
+// build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -I flash_attention_from_scratch_b200/csrc
+//        -o tools/softmax_probe tools/softmax_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "softmax_sm100.cuh"
+
+using namespace fa;
+
+template <bool kBF16, int kEmu, int kEmuLast, int kVariant, bool kSplit>
+__global__ void __launch_bounds__(384, 1)
+probe(unsigned long long* out, int iters, int active_wgs, float c) {
+    __shared__ uint32_t tmem_ptr;
+    __shared__ unsigned long long dummy_bar[4];
+    extern __shared__ uint8_t pad[];  // forces 1 CTA / SM
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wg = warp >> 2;
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&dummy_bar[i]), 4);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(&tmem_ptr), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    if (wg == 2) {
+        setmaxnreg_dec<88>();
+    } else {
+        setmaxnreg_inc<208>();
+        if (wg < active_wgs) {
+            const int s = wg;
+            const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+            const uint32_t t_s = tmem_base + lane_sel + s * 128;
+            const uint32_t t_p = tmem_base + lane_sel + 256 + s * 128;  // scratch (O region)
+            // fill S with plausible scores: N(0, 11) like q.k of unit gaussians at d = 128
+            {
+                uint32_t v[32];
+                uint32_t st = 1234567u + threadIdx.x * 7919u + blockIdx.x * 104729u;
+                for (int q = 0; q < 4; ++q) {
+                    for (int i = 0; i < 32; ++i) {
+                        st = st * 1664525u + 1013904223u;
+                        const float u = (float)(st >> 8) * (1.0f / 16777216.0f);
+                        v[i] = __float_as_uint((u - 0.5f) * 40.0f);
+                    }
+                    tmem_st_32x32b_x32(t_s + q * 32, v);
+                }
+                tmem_wait_st();
+            }
+            float m_run = -INFINITY, l_run = 0.f;
+            unsigned long long t_ld = 0, t_max = 0, t_exp = 0;
+            const unsigned long long t_begin = clock64();
+            for (int j = 0; j < iters; ++j) {
+                const unsigned long long t0 = clock64();
+                uint32_t sr[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+                tmem_wait_ld();
+                const unsigned long long t1 = clock64();
+                float mx = fmaxf(row_max_128(sr), m_run);
+                float alpha = 1.f;
+                if (j == 0) {
+                    m_run = mx;
+                } else {
+                    const float delta = (mx - m_run) * c;
+                    const bool need = delta > 8.0f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) {
+                            alpha = ex2_approx(-delta);
+                            m_run = mx;
+                        }
+                    }
+                }
+                const unsigned long long t2 = clock64();
+                const float neg_mc = -m_run * c;
+                const float2 c2 = make_float2(c, c), nm2 = make_float2(neg_mc, neg_mc);
+                float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[16];
+                    if (q == 3) exp_fragment<kBF16, kEmuLast, kVariant>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    else exp_fragment<kBF16, kEmu, kVariant>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    tmem_st_32x32b_x16(t_p + q * 16, pk);
+                    if (kSplit && q == 2) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&dummy_bar[s]));
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&dummy_bar[2 + s]));
+                l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
+                const unsigned long long t3 = clock64();
+                t_ld += t1 - t0;
+                t_max += t2 - t1;
+                t_exp += t3 - t2;
+            }
+            const unsigned long long t_end = clock64();
+            if (lane == 0) {
+                unsigned long long* o = out + (blockIdx.x * 8 + warp) * 4;
+                o[0] = (t_end - t_begin);
+                o[1] = t_ld;
+                o[2] = t_max;
+                o[3] = t_exp + (unsigned long long)(l_run != 12345.f ? 0 : 1);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int kEmu, int kEmuLast, int kVariant, bool kSplit>
+void run(const char* name, int wgs) {
+    const int iters = 2000, n_sm = 148;
+    unsigned long long* d;
+    cudaMalloc(&d, n_sm * 8 * 4 * sizeof(unsigned long long));
+    cudaMemset(d, 0, n_sm * 8 * 4 * sizeof(unsigned long long));
+    auto kern = probe<true, kEmu, kEmuLast, kVariant, kSplit>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const float c = 1.4426950408889634f / 11.313708498984761f;
+    for (int rep = 0; rep < 2; ++rep) kern<<<n_sm, 384, 200 * 1024>>>(d, iters, wgs, c);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("%s: CUDA error %s\n", name, cudaGetErrorString(e));
+        exit(1);
+    }
+    static unsigned long long h[148 * 8 * 4];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    double tot = 0, ld = 0, mx = 0, ex = 0;
+    int n = 0;
+    for (int b = 0; b < n_sm; ++b)
+        for (int w = 0; w < 4 * wgs; ++w) {
+            const unsigned long long* o = h + (b * 8 + w) * 4;
+            tot += (double)o[0] / iters;
+            ld += (double)o[1] / iters;
+            mx += (double)o[2] / iters;
+            ex += (double)o[3] / iters;
+            ++n;
+        }
+    printf("%-28s wgs=%d  cycles/block: total %7.1f  ld %6.1f  max %6.1f  exp+st %7.1f   (%.2f clk/elem/warp)\n",
+           name, wgs, tot / n, ld / n, mx / n, ex / n, tot / n / 128.0);
+    cudaFree(d);
+}
+
+#define RUN(E, EL, V, SP)                                         \
+    run<E, EL, V, SP>("emu" #E "/last" #EL "/var" #V "/split" #SP, 1); \
+    run<E, EL, V, SP>("emu" #E "/last" #EL "/var" #V "/split" #SP, 2);
+
+int main() {
+    RUN(0, 0, 0, true)
+    RUN(2, 0, 0, true)
+    RUN(4, 0, 0, true)
+    RUN(4, 4, 0, true)
+    RUN(6, 6, 0, true)
+    RUN(8, 8, 0, true)
+    RUN(16, 16, 0, true)
+    RUN(0, 0, 1, true)
+    RUN(4, 4, 1, true)
+    RUN(8, 8, 1, true)
+    RUN(0, 0, 0, false)
+    RUN(4, 4, 0, false)
+    return 0;
+}
