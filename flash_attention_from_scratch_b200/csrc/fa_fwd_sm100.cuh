@@ -63,6 +63,10 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #ifndef FA_EMU_PAIRS_LAST
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
 #endif
+#ifndef FA_PINGPONG
+#define FA_PINGPONG 1         // 1: the two softmax warpgroups take turns on the exp2 phase (token
+                              // passed through named barriers 3/4) instead of contending for MUFU
+#endif
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
 #endif
@@ -77,10 +81,6 @@ constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
 constexpr bool kSplitP = FA_SPLIT_P != 0;
 constexpr bool kPingPong = FA_PINGPONG != 0;
 static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
-#ifndef FA_PINGPONG
-#define FA_PINGPONG 1         // 1: the two softmax warpgroups take turns on the exp2 phase (token
-                              // passed through named barriers 3/4) instead of contending for MUFU
-#endif
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
