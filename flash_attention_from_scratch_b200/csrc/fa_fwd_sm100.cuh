@@ -64,7 +64,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
 #endif
 #ifndef FA_PINGPONG
-#define FA_PINGPONG 1         // 1: the two softmax warpgroups take turns on the exp2 phase (token
+#define FA_PINGPONG 0         // 1: the two softmax warpgroups take turns on the exp2 phase (token; measured: no gain,
                               // passed through named barriers 3/4) instead of contending for MUFU
 #endif
 #ifndef FA_SPLIT_P
