@@ -282,7 +282,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         nbytes = hq.numel() * hq.element_size()
         e2e = {"value": global_flops / te.item() / 1e12, "unit": UNIT,
-               "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": nbytes,
+               "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
                "path": "fa_fwd_host (C ABI): pinned host Q,K,V -> HBM, kernel, O -> pinned host; "
                        "batch-pipelined copies inside the timed region"}

@@ -421,6 +421,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             for (int j = 0; j < n_iter; ++j, ++g) {
                 mbar_wait(s_full(s), g & 1u, 300 + s);
                 tc_fence_after();
+                if (FA_PINGPONG == 2 && level >= 4) named_bar_sync(3 + s, 256);  // whole step exclusive
                 uint32_t* tr = nullptr;
                 if constexpr (kDebug) {
                     if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
@@ -478,7 +479,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const float2 c2 = make_float2(c, c);
                 const float2 nm2 = make_float2(neg_mc, neg_mc);
                 float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-                if (kPingPong && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
+                if (kPingPong && FA_PINGPONG == 1 && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];

@@ -12,12 +12,11 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "pp_emu0": {"FA_EMU_PAIRS": 0},
-    "pp_emu4": {"FA_EMU_PAIRS": 4},
-    "pp_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
-    "pp_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
-    "pp_emu8_8": {"FA_EMU_PAIRS": 8, "FA_EMU_PAIRS_LAST": 8},
-    "nopp_emu4": {"FA_EMU_PAIRS": 4, "FA_PINGPONG": 0},
+    "base_emu4": {"FA_EMU_PAIRS": 4},
+    "pp2_emu4": {"FA_EMU_PAIRS": 4, "FA_PINGPONG": 2},
+    "pp2_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6, "FA_PINGPONG": 2},
+    "pp2_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4, "FA_PINGPONG": 2},
+    "pp2_emu0": {"FA_EMU_PAIRS": 0, "FA_PINGPONG": 2},
 }
 
 

@@ -16,7 +16,75 @@
 
 using namespace fa;
 
-template <bool kBF16, int kEmu, int kEmuLast, int kVariant, bool kSplit>
+namespace fa {
+// EXPERIMENT (not used by the production kernel; results in profiles/r01_softmax_probe_notes.md):
+// One KV block of online softmax for one row (128 S values in registers).
+//
+// kFirst (first block of a tile): m = rowmax, P = exp2(S*c - m*c).
+// Otherwise SPECULATIVE: the first three fragments are exponentiated against the running (stale)
+// max while the row-max chain of this block executes in their shadow (FMNMX on the ALU pipe, exp2 on
+// MUFU/FMA); only if some row of the warp grew by more than `threshold` (log2 units) the accumulator
+// is rescaled and those fragments are redone against the new max -- rare, and exact either way
+// because P is only published (arrive_part) after the check.  Until then P <= 2^threshold.
+//   store_p(q, pk)   : write 16 packed P columns of fragment q
+//   arrive_part(last): publish P (first three fragments, then the last one)
+//   rescale_o(alpha) : multiply this row of the O accumulator by alpha (only called on the slow path)
+template <bool kBF16, int kEmu, int kEmuLast, int kVariant, bool kFirst, class StoreP, class ArrivePart,
+          class RescaleO>
+__device__ __forceinline__ void softmax_block(const uint32_t (&sr)[4][32], float c, float threshold,
+                                              float& m_run, float& l_run, StoreP&& store_p,
+                                              ArrivePart&& arrive_part, RescaleO&& rescale_o) {
+    const float mx = fmaxf(row_max_128(sr), m_run);
+    const float2 c2 = make_float2(c, c);
+    float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+    float alpha = 1.f;
+    if constexpr (kFirst) m_run = mx;
+    {
+        const float neg_mc = -m_run * c;
+        const float2 nm2 = make_float2(neg_mc, neg_mc);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint32_t pk[16];
+            exp_fragment<kBF16, kEmu, kVariant>(sr[q], c2, nm2, sum_a, sum_b, pk);
+            store_p(q, pk);
+        }
+    }
+    if constexpr (!kFirst) {
+        const float delta = (mx - m_run) * c;  // >= 0
+        const bool need = delta > threshold;
+        if (__any_sync(0xffffffffu, need)) {   // slow path: some row of this warp outgrew the stale max
+            if (need) {
+                alpha = ex2_approx(-delta);
+                m_run = mx;
+            }
+            rescale_o(alpha);
+            sum_a = make_float2(0.f, 0.f);
+            sum_b = make_float2(0.f, 0.f);
+            const float neg_mc = -m_run * c;
+            const float2 nm2 = make_float2(neg_mc, neg_mc);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                uint32_t pk[16];
+                exp_fragment<kBF16, kEmu, kVariant>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                store_p(q, pk);
+            }
+        }
+    }
+    arrive_part(false);
+    {
+        const float neg_mc = -m_run * c;
+        const float2 nm2 = make_float2(neg_mc, neg_mc);
+        uint32_t pk[16];
+        exp_fragment<kBF16, kEmuLast, kVariant>(sr[3], c2, nm2, sum_a, sum_b, pk);
+        store_p(3, pk);
+    }
+    arrive_part(true);
+    l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
+}
+
+}  // namespace fa
+
+template <bool kBF16, int kEmu, int kEmuLast, int kVariant, bool kSplit, bool kSpec = false>
 __global__ void __launch_bounds__(384, 1)
 probe(unsigned long long* out, int iters, int active_wgs, float c) {
     __shared__ uint32_t tmem_ptr;
@@ -69,6 +137,26 @@ probe(unsigned long long* out, int iters, int active_wgs, float c) {
                 for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
                 tmem_wait_ld();
                 const unsigned long long t1 = clock64();
+                if constexpr (kSpec) {
+                    auto store_p = [&](int q, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(t_p + q * 16, pk); };
+                    auto arrive_part = [&](bool last) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&dummy_bar[(last ? 2 : 0) + s]));
+                    };
+                    auto rescale_o = [&](float) {};
+                    if (j == 0)
+                        softmax_block<kBF16, kEmu, kEmuLast, kVariant, true>(sr, c, 8.0f, m_run, l_run, store_p,
+                                                                             arrive_part, rescale_o);
+                    else
+                        softmax_block<kBF16, kEmu, kEmuLast, kVariant, false>(sr, c, 8.0f, m_run, l_run, store_p,
+                                                                              arrive_part, rescale_o);
+                    const unsigned long long t3s = clock64();
+                    t_ld += t1 - t0;
+                    t_exp += t3s - t1;
+                    continue;
+                }
                 float mx = fmaxf(row_max_128(sr), m_run);
                 float alpha = 1.f;
                 if (j == 0) {
@@ -128,13 +216,13 @@ probe(unsigned long long* out, int iters, int active_wgs, float c) {
     }
 }
 
-template <int kEmu, int kEmuLast, int kVariant, bool kSplit>
+template <int kEmu, int kEmuLast, int kVariant, bool kSplit, bool kSpec = false>
 void run(const char* name, int wgs) {
     const int iters = 2000, n_sm = 148;
     unsigned long long* d;
     cudaMalloc(&d, n_sm * 8 * 4 * sizeof(unsigned long long));
     cudaMemset(d, 0, n_sm * 8 * 4 * sizeof(unsigned long long));
-    auto kern = probe<true, kEmu, kEmuLast, kVariant, kSplit>;
+    auto kern = probe<true, kEmu, kEmuLast, kVariant, kSplit, kSpec>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const float c = 1.4426950408889634f / 11.313708498984761f;
     for (int rep = 0; rep < 2; ++rep) kern<<<n_sm, 384, 200 * 1024>>>(d, iters, wgs, c);
@@ -165,18 +253,20 @@ void run(const char* name, int wgs) {
     run<E, EL, V, SP>("emu" #E "/last" #EL "/var" #V "/split" #SP, 1); \
     run<E, EL, V, SP>("emu" #E "/last" #EL "/var" #V "/split" #SP, 2);
 
+#define RUNS(E, EL)                                                   \
+    run<E, EL, 0, true, true>("SPEC emu" #E "/last" #EL, 1);           \
+    run<E, EL, 0, true, true>("SPEC emu" #E "/last" #EL, 2);
+
 int main() {
     RUN(0, 0, 0, true)
-    RUN(2, 0, 0, true)
     RUN(4, 0, 0, true)
-    RUN(4, 4, 0, true)
     RUN(6, 6, 0, true)
-    RUN(8, 8, 0, true)
-    RUN(16, 16, 0, true)
-    RUN(0, 0, 1, true)
-    RUN(4, 4, 1, true)
-    RUN(8, 8, 1, true)
-    RUN(0, 0, 0, false)
-    RUN(4, 4, 0, false)
+    RUNS(0, 0)
+    RUNS(2, 0)
+    RUNS(4, 0)
+    RUNS(4, 4)
+    RUNS(6, 0)
+    RUNS(6, 6)
+    RUNS(8, 8)
     return 0;
 }
