@@ -163,11 +163,8 @@ int validate(const Problem& p, int d_head) {
     if (!p.q || !p.k || !p.v || !p.o) return fail(FA_ERR_ARG, "null tensor pointer");
     if (p.B <= 0 || p.N <= 0 || p.H <= 0)
         return fail(FA_ERR_ARG, "batch, seq_len and n_heads must be positive");
-    if (p.N % fa::kBlockN != 0)
-        return fail(FA_ERR_SEQLEN,
-                    "Only multiples of B_r are supported for seq_len Q currently (B_r = B_c = 128, "
-                    "seq_len = %d)",
-                    p.N);
+    if (p.N > (1 << 24))
+        return fail(FA_ERR_SEQLEN, "seq_len %d is out of range (max %d)", p.N, 1 << 24);
     const uintptr_t a = reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.k) |
                         reinterpret_cast<uintptr_t>(p.v) | reinterpret_cast<uintptr_t>(p.o);
     if (a & 15) return fail(FA_ERR_ARG, "tensor pointers must be 16-byte aligned");
@@ -193,7 +190,7 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     prm.batch = p.B;
     prm.seq_len = p.N;
     prm.n_heads = p.H;
-    prm.n_kv_blocks = p.N / fa::kBlockN;
+    prm.n_kv_blocks = (p.N + fa::kBlockN - 1) / fa::kBlockN;
     prm.n_q_pairs = (p.N + fa::kQStages * fa::kBlockM - 1) / (fa::kQStages * fa::kBlockM);
     prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
 

@@ -111,7 +111,7 @@ struct FwdParams {
     int batch;
     int seq_len;
     int n_heads;
-    int n_kv_blocks;   // seq_len / 128
+    int n_kv_blocks;   // ceil(seq_len / 128); keys beyond seq_len in the last block are masked
     int n_q_pairs;     // ceil(seq_len / 256): work tiles per (batch, head)
     int n_tiles;       // batch * n_heads * n_q_pairs
     float scale_log2;  // log2(e) / sqrt(d_head)
@@ -407,6 +407,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const uint32_t t_p = t_s;
         const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim;
         const float c = prm.scale_log2;
+        const int kv_tail = prm.seq_len & (kBlockN - 1);  // valid keys in the last block (0 = all)
         uint32_t g = 0;  // KV blocks processed so far (all tiles)
         int it = 0;
         // exp2-phase token (softmax_probe: one warpgroup alone needs ~1400 cycles per block, two
@@ -435,6 +436,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 tmem_wait_ld();
                 if constexpr (kDebug) {
                     if (tr) tr[1] = clk32();
+                }
+                // ragged tail (seq_len % 128 != 0, beyond the reference's contract): TMA zero-filled
+                // the missing K/V rows; their scores are forced to -inf so that P = 0 exactly.
+                if (j + 1 == n_blocks && kv_tail != 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (q * 32 + i >= kv_tail) sr[q][i] = 0xff800000u;
+                    }
                 }
 
                 if constexpr (kDebug) {

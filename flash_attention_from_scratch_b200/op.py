@@ -57,8 +57,17 @@ def _prepare(kernel_cfg, q, k, v, o):
         raise RuntimeError("Query and key tensors have same shape")
     if q.shape != v.shape:
         raise RuntimeError("Query and value tensors have same shape")
-    if q.size(1) % 128 != 0:
+    # The reference requires seq_len % B_r == 0 and % B_c == 0 (flash_attention.cu:79-82).  Kept
+    # verbatim when a reference-style config is passed; with kernel_cfg=None any seq_len >= 1 runs
+    # (the kernel masks the ragged tail), an extension beyond the reference.
+    b_r = getattr(kernel_cfg, "B_r", None) if kernel_cfg is not None else None
+    b_c = getattr(kernel_cfg, "B_c", None) if kernel_cfg is not None else None
+    if b_r and q.size(1) % b_r != 0:
         raise RuntimeError("Only multiples of B_r are supported for seq_len Q currently")
+    if b_c and q.size(1) % b_c != 0:
+        raise RuntimeError("Only multiples of B_c are supported for seq_len K currently")
+    if q.size(1) < 1:
+        raise RuntimeError("seq_len must be positive")
     if o is not None:
         if o.dtype != q.dtype:
             raise RuntimeError("Output tensor must have the same dtype as inputs")

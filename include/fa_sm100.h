@@ -11,8 +11,10 @@
  *   Q, K, V, O are 16-bit (fp16 or bf16) device tensors of logical shape
  *   (batch, seq_len, n_heads, d_head) with d_head == 128 contiguous; the other three strides are
  *   given in ELEMENTS (as torch's Tensor.stride()) and shared by all four tensors, exactly as the
- *   reference takes them from Q only (flash_attention.cu:84-86).  seq_len must be a multiple of
- *   128 (the reference requires a multiple of its B_r/B_c tile, flash_attention.cu:79-82).
+ *   reference takes them from Q only (flash_attention.cu:84-86).  Any seq_len >= 1 is accepted
+ *   (keys beyond seq_len in the last 128-block are masked to -inf); the reference requires a
+ *   multiple of its B_r/B_c tile (flash_attention.cu:79-82) and the Python operator keeps that
+ *   check when it is given a reference-style kernel_cfg.
  *   Unlike the reference kernel (static_kernel_configuration.cuh:146: row stride hard-coded to
  *   d_head * 16) any n_heads and any 16-byte-aligned strides are accepted.
  *
@@ -37,7 +39,8 @@ extern "C" {
 #define FA_OK 0
 #define FA_ERR_DTYPE 1      /* "Only fp16 and bf16 are supported"            flash_attention.cu:51-52 */
 #define FA_ERR_DHEAD 2      /* d_head != 128 ("Kernel configuration was not found", :60-61)        */
-#define FA_ERR_SEQLEN 3     /* seq_len not a multiple of the tile           flash_attention.cu:79-82 */
+#define FA_ERR_SEQLEN 3     /* seq_len out of range (the B_r/B_c multiple check of flash_attention.cu:79-82
+                               lives in the Python operator)                                        */
 #define FA_ERR_ARG 4        /* null pointer / non-positive size / misaligned pointer or stride     */
 #define FA_ERR_DEVICE 5     /* not an sm_100 device / no CUDA driver ("requires SM_80", :46-48)    */
 #define FA_ERR_TENSORMAP 6  /* cuTensorMapEncodeTiled rejected the layout                          */

@@ -58,7 +58,7 @@ def test_c_abi_argument_validation_without_gpu(lib):
                          kw.get("dtype", 15), None)
     assert lib.fa_fwd(*args(dtype=6)) == 1 and "Only fp16 and bf16" in _lib.last_error()
     assert lib.fa_fwd(*args(D=64)) == 2 and "Kernel configuration was not found" in _lib.last_error()
-    assert lib.fa_fwd(*args(N=192)) == 3 and "multiples of B_r" in _lib.last_error()
+    assert lib.fa_fwd(*args(N=(1 << 24) + 1)) == 3 and "out of range" in _lib.last_error()
     assert lib.fa_fwd(*args(B=0)) == 4
     assert lib.fa_fwd(*args(sn=100)) == 4 and "strides" in _lib.last_error()
     a = list(args())

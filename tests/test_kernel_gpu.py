@@ -140,6 +140,43 @@ def test_long_sequences_fp16_vs_bf16(N, B):
     assert errs[torch.float16] < errs[torch.bfloat16]
 
 
+# ------------------------------------------------------------------ ragged seq_len
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,N,H", [(1, 1, 1), (2, 77, 3), (1, 129, 2), (2, 200, 5), (1, 1000, 4),
+                                   (1, 4095, 2), (3, 333, 40)])
+def test_ragged_seq_len(dtype, B, N, H):
+    # beyond the reference (which needs seq_len % B_r == 0): kernel_cfg=None accepts any seq_len
+    q, k, v = rand_qkv((B, N, H, 128), dtype, seed=N)
+    out = flash_attention.forward(None, q, k, v)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), sdpa32(q, k, v), **north_star_tol(N))
+    ok, d_out, d_ref = reference_pass_criterion(out, py_flash_attention(q, k, v, False),
+                                                py_flash_attention(q, k, v, True))
+    assert ok, (d_out, d_ref)
+
+
+def test_ragged_tail_never_reads_past_seq_len(lib):
+    # NaN-poisoned rows right behind every sequence: through the C ABI with the padded strides the
+    # result must equal the contiguous run bit for bit (TMA bounds = seq_len, tail keys masked)
+    from flash_attention_from_scratch_b200 import _lib
+    B, N, H, pad = 2, 300, 3, 84
+    q, k, v = rand_qkv((B, N, H, 128), torch.bfloat16, seed=21)
+    ref = flash_attention.forward(None, q, k, v)
+    bufs = []
+    for t in (q, k, v):
+        big = torch.full((B, N + pad, H, 128), float("nan"), device=DEV, dtype=torch.bfloat16)
+        big[:, :N] = t
+        bufs.append(big)
+    obig = torch.zeros((B, N + pad, H, 128), device=DEV, dtype=torch.bfloat16)
+    sb, sn, sh, _ = obig.stride()
+    rc = lib.fa_fwd(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), obig.data_ptr(), B, N, H, 128,
+                    sb, sn, sh, 15, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(obig[:, :N], ref)
+    assert (obig[:, N:] == 0).all()
+
+
 # ------------------------------------------------------------------ edge cases
 def test_rescale_path_growing_scores():
     # scores that keep growing along the key axis: every KV block raises the row max by far more
@@ -198,8 +235,9 @@ def test_operator_errors_match_reference():
         flash_attention.forward(None, q.transpose(1, 2), k, v)
     with pytest.raises(RuntimeError, match="same shape"):
         flash_attention.forward(None, q, k[:, :128].contiguous(), v)
-    with pytest.raises(RuntimeError, match="multiples of B_r"):
-        flash_attention.forward(None, q[:, :192].contiguous(), k[:, :192].contiguous(), v[:, :192].contiguous())
+    with pytest.raises(RuntimeError, match="multiples of B_r"):   # reference-style config: same check
+        flash_attention.forward(cfg_for(torch.bfloat16), q[:, :192].contiguous(), k[:, :192].contiguous(),
+                                v[:, :192].contiguous())
     with pytest.raises(RuntimeError, match="not found"):
         flash_attention.forward(None, q[..., :64].contiguous(), k[..., :64].contiguous(), v[..., :64].contiguous())
 
