@@ -70,9 +70,9 @@ struct DeviceState {
 };
 DeviceState g_dev[kMaxDevices];
 
-template <bool kBF16, bool kDebug>
+template <bool kBF16, bool kDebug, bool kRagged>
 cudaError_t set_smem_attr() {
-    return cudaFuncSetAttribute(fa::fa_fwd_kernel<kBF16, kDebug>,
+    return cudaFuncSetAttribute(fa::fa_fwd_kernel<kBF16, kDebug, kRagged>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
 }
 
@@ -109,10 +109,12 @@ int init_device(int dev) {
         int cur = -1;
         cudaGetDevice(&cur);
         if (cur != dev) cudaSetDevice(dev);
-        e = set_smem_attr<true, false>();
-        if (e == cudaSuccess) e = set_smem_attr<false, false>();
-        if (e == cudaSuccess) e = set_smem_attr<true, true>();
-        if (e == cudaSuccess) e = set_smem_attr<false, true>();
+        e = set_smem_attr<true, false, false>();
+        if (e == cudaSuccess) e = set_smem_attr<false, false, false>();
+        if (e == cudaSuccess) e = set_smem_attr<true, false, true>();
+        if (e == cudaSuccess) e = set_smem_attr<false, false, true>();
+        if (e == cudaSuccess) e = set_smem_attr<true, true, true>();
+        if (e == cudaSuccess) e = set_smem_attr<false, true, true>();
         if (cur != dev && cur >= 0) cudaSetDevice(cur);
         if (e != cudaSuccess) {
             st.status = FA_ERR_LAUNCH;
@@ -200,12 +202,16 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     // persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
     dim3 grid((unsigned)(n_tiles < n_sms ? n_tiles : n_sms)), block(fa::kNumThreads);
-    if (p.dtype == FA_DTYPE_BF16)
-        fa::fa_fwd_kernel<true, kDebug>
-            <<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
-    else
-        fa::fa_fwd_kernel<false, kDebug>
-            <<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
+    // one instantiation per (dtype, ragged tail?); the debug build always carries the masking code
+    const bool ragged = kDebug || (p.N % fa::kBlockN) != 0;
+    auto go = [&](auto kern) { kern<<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg); };
+    if (p.dtype == FA_DTYPE_BF16) {
+        if (ragged) go(fa::fa_fwd_kernel<true, kDebug, true>);
+        else go(fa::fa_fwd_kernel<true, false, false>);
+    } else {
+        if (ragged) go(fa::fa_fwd_kernel<false, kDebug, true>);
+        else go(fa::fa_fwd_kernel<false, false, false>);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     FA_CUDA(cudaGetLastError());
     return FA_OK;

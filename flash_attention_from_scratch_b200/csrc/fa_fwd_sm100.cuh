@@ -40,7 +40,10 @@ constexpr int kBlockM = 128;   // query rows per Q tile == TMEM lanes
 constexpr int kBlockN = 128;   // key/value rows per block
 constexpr int kHeadDim = 128;  // d_head (the only one the reference supports, README.md:9-15)
 constexpr int kQStages = 2;    // Q tiles per work tile
-constexpr int kKVStages = 4;   // K/V ring slots (each slot holds one K block or one V block)
+#ifndef FA_KV_STAGES
+#define FA_KV_STAGES 4
+#endif
+constexpr int kKVStages = FA_KV_STAGES;  // K/V ring slots (each slot holds one K block or one V block)
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
 constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
@@ -117,7 +120,9 @@ struct FwdParams {
     float scale_log2;  // log2(e) / sqrt(d_head)
 };
 
-template <bool kBF16, bool kDebug>
+// kRagged: seq_len % 128 != 0 (tail keys masked); a separate instantiation because the masking
+// code costs 1.6 % at the headline even when never taken (profiles/r01_sweep9_ragged_ab.json).
+template <bool kBF16, bool kDebug, bool kRagged>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -439,7 +444,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 }
                 // ragged tail (seq_len % 128 != 0, beyond the reference's contract): TMA zero-filled
                 // the missing K/V rows; their scores are forced to -inf so that P = 0 exactly.
-                if (j + 1 == n_blocks && kv_tail != 0) {
+                if (kRagged && j + 1 == n_blocks && kv_tail != 0) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
 #pragma unroll

@@ -34,7 +34,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma(lib):
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.lib_path())], capture_output=True,
                           text=True).stdout
     assert "EF_CUDA_SM100" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
         assert mnemonic in sass, mnemonic
     assert "HMMA." not in sass  # no legacy mma.sync path
 

@@ -12,11 +12,11 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "base_emu4": {"FA_EMU_PAIRS": 4},
-    "pp2_emu4": {"FA_EMU_PAIRS": 4, "FA_PINGPONG": 2},
-    "pp2_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6, "FA_PINGPONG": 2},
-    "pp2_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4, "FA_PINGPONG": 2},
-    "pp2_emu0": {"FA_EMU_PAIRS": 0, "FA_PINGPONG": 2},
+    "prod": {},
+    "noragged": {"FA_RAGGED": 0},
+    "emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "r216": {"FA_REGS_SOFTMAX": 216, "FA_REGS_CTRL": 72},
+    "kv3": {"FA_KV_STAGES": 3},
 }
 
 
