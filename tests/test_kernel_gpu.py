@@ -272,3 +272,43 @@ def test_launch_counter_counts_our_kernel(lib):
     n0 = _lib.launch_count()
     flash_attention.forward(None, q, k, v)
     assert _lib.launch_count() == n0 + 1
+
+
+def test_concurrent_threads_and_streams():
+    # the library is re-entrant: two host threads, each on its own stream, same results as serial
+    import threading
+    q, k, v = rand_qkv((2, 1024, 8, 128), torch.bfloat16, seed=31)
+    ref = flash_attention.forward(None, q, k, v)
+    torch.cuda.synchronize()
+    outs, errs = [None, None], []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(5):
+                    outs[i] = flash_attention.forward(None, q, k, v)
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_second_device_and_shard_plan():
+    # (batch x heads) sharding: each device computes its shard independently; union == unsharded
+    from flash_attention_from_scratch_b200.shard import plan_shards
+    B, N, H = 4, 512, 6
+    q, k, v = rand_qkv((B, N, H, 128), torch.bfloat16, seed=41)
+    ref = flash_attention.forward(None, q, k, v)
+    full = torch.empty_like(ref)
+    for sh in plan_shards(B, H, 2):
+        dev = f"cuda:{sh.rank}"
+        qs, ks, vs = (sh.take(t).contiguous().to(dev) for t in (q, k, v))
+        full[sh.b0:sh.b1, :, sh.h0:sh.h1] = flash_attention.forward(None, qs, ks, vs).to(DEV)
+    assert torch.equal(full, ref)
