@@ -196,6 +196,26 @@ def test_rescale_path_growing_scores():
         assert ok, (dtype, d_out, d_ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("scale", [3.0, 20.0])
+def test_overflowing_speculation_takes_exact_path(dtype, scale):
+    # scores so large that exponentiating against a stale max overflows (inf / garbage): the kernel
+    # must notice (row sum / tracked max checks) and redo the block exactly
+    g = torch.Generator(device=DEV).manual_seed(13)
+    N = 1024
+    q = (torch.randn(1, N, 2, 128, device=DEV, generator=g) * scale).to(dtype)
+    k = (torch.randn(1, N, 2, 128, device=DEV, generator=g) * scale).to(dtype)
+    # make later key blocks systematically larger so the running max keeps being outgrown
+    k = (k.float() * torch.linspace(0.2, 1.0, N, device=DEV).view(1, N, 1, 1)).to(dtype)
+    v = torch.randn(1, N, 2, 128, device=DEV, generator=g).to(dtype)
+    out = flash_attention.forward(None, q, k, v)
+    assert torch.isfinite(out.float()).all()
+    ok, d_out, d_ref = reference_pass_criterion(out, py_flash_attention(q, k, v, False),
+                                                py_flash_attention(q, k, v, True))
+    assert ok, (d_out, d_ref)
+    torch.testing.assert_close(out.float(), sdpa32(q, k, v), rtol=2e-2, atol=4e-3)
+
+
 def test_large_magnitude_and_constant_inputs():
     q, k, v = rand_qkv((1, 512, 2, 128), torch.bfloat16, seed=9, scale=6.0)   # |S| up to ~1e3 * ...
     out = flash_attention.forward(None, q, k, v)
