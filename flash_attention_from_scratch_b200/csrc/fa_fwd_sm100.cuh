@@ -70,9 +70,6 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_PINGPONG 0         // 1: the two softmax warpgroups take turns on the exp2 phase (token; measured: no gain,
                               // passed through named barriers 3/4) instead of contending for MUFU
 #endif
-#ifndef FA_NOMAX
-#define FA_NOMAX 1            // 1: blocks after the first skip the up-front row max (softmax_block_nomax)
-#endif
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
 #endif
@@ -465,101 +462,67 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     }
                     if (level == 3) break;
                 }
-                auto rescale_o = [&](float a) {
-                    // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
+                float mx = row_max_128(sr);
+                mx = fmaxf(mx, m_run);
+                float alpha = 1.f;
+                if (j == 0) {
+                    m_run = mx;
+                } else {
+                    const float delta = (mx - m_run) * c;  // >= 0
+                    const bool need = delta > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) {
+                            alpha = ex2_approx(-delta);
+                            m_run = mx;
+                        }
+                        // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t o[32];
-                        tmem_ld_32x32b_x32(t_o + q * 32, o);
-                        tmem_wait_ld();
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t o[32];
+                            tmem_ld_32x32b_x32(t_o + q * 32, o);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a);
-                        tmem_st_32x32b_x32(t_o + q * 32, o);
+                            for (int i = 0; i < 32; ++i)
+                                o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32b_x32(t_o + q * 32, o);
+                        }
                     }
-                };
-                if (FA_NOMAX && kSplitP && j > 0) {
-                    auto store_p = [&](int q, const uint32_t (&pk)[16]) {
-                        tmem_st_32x32b_x16(t_p + q * 16, pk);
-                    };
-                    auto arrive_part = [&](bool last) {
+                }
+                if constexpr (kDebug) {
+                    if (tr) tr[2] = clk32();
+                }
+                const float neg_mc = -m_run * c;
+                const float2 c2 = make_float2(c, c);
+                const float2 nm2 = make_float2(neg_mc, neg_mc);
+                float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+                if (kPingPong && FA_PINGPONG == 1 && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[16];
+                    if (q == 3)
+                        exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    else
+                        exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    tmem_st_32x32b_x16(t_p + q * 16, pk);
+                    if (kSplitP && q == 2) {
                         tmem_wait_st();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(last ? p_last(s) : p_full(s));
+                        if (lane == 0) mbar_arrive(p_full(s));
                         if constexpr (kDebug) {
-                            if (tr) tr[last ? 4 : 3] = clk32();
-                        }
-                    };
-                    if constexpr (kDebug) {
-                        if (tr) tr[2] = clk32();
-                    }
-                    softmax_block_nomax<kBF16, kEmuPairs, kEmuPairsLast>(sr, c, kRescaleThreshold, m_run,
-                                                                         l_run, store_p, arrive_part,
-                                                                         rescale_o);
-                    if (kPingPong && level >= 4) named_bar_arrive(3 + (s ^ 1), 256);
-                } else {
-                    float mx = row_max_128(sr);
-                    mx = fmaxf(mx, m_run);
-                    float alpha = 1.f;
-                    if (j == 0) {
-                        m_run = mx;
-                    } else {
-                        const float delta = (mx - m_run) * c;  // >= 0
-                        const bool need = delta > kRescaleThreshold;
-                        if (__any_sync(0xffffffffu, need)) {
-                            if (need) {
-                                alpha = ex2_approx(-delta);
-                                m_run = mx;
-                            }
-                            // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
-    #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t o[32];
-                                tmem_ld_32x32b_x32(t_o + q * 32, o);
-                                tmem_wait_ld();
-    #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                                tmem_st_32x32b_x32(t_o + q * 32, o);
-                            }
+                            if (tr) tr[3] = clk32();
                         }
                     }
-                    if constexpr (kDebug) {
-                        if (tr) tr[2] = clk32();
-                    }
-                    const float neg_mc = -m_run * c;
-                    const float2 c2 = make_float2(c, c);
-                    const float2 nm2 = make_float2(neg_mc, neg_mc);
-                    float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-                    if (kPingPong && FA_PINGPONG == 1 && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
-    #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t pk[16];
-                        if (q == 3)
-                            exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
-                        else
-                            exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
-                        tmem_st_32x32b_x16(t_p + q * 16, pk);
-                        if (kSplitP && q == 2) {
-                            tmem_wait_st();
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(p_full(s));
-                            if constexpr (kDebug) {
-                                if (tr) tr[3] = clk32();
-                            }
-                        }
-                    }
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
-                    if (kPingPong && level >= 4) named_bar_arrive(3 + (s ^ 1), 256);  // pass the token
-                    if constexpr (kDebug) {
-                        if (tr) tr[4] = clk32();
-                    }
-                    l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
                 }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
+                if (kPingPong && level >= 4) named_bar_arrive(3 + (s ^ 1), 256);  // pass the token
+                if constexpr (kDebug) {
+                    if (tr) tr[4] = clk32();
+                }
+                l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
             }
 
             // ------------------------------- epilogue ------------------------------------

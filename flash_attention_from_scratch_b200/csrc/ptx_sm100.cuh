@@ -321,13 +321,6 @@ __device__ __forceinline__ float2 ex2_emulated_x2(float2 x) {
     return out;
 }
 
-// Same as ex2_emulated_x2 but also folds the two inputs into a running max `xmax` (one FMNMX3):
-// lets the caller verify afterwards that no emulated input exceeded the range it assumed.
-__device__ __forceinline__ float2 ex2_emulated_x2_track(float2 x, float& xmax) {
-    xmax = fmaxf(fmaxf(xmax, x.x), x.y);
-    return ex2_emulated_x2(x);
-}
-
 // Packs two fp32 into one 32-bit register of two 16-bit floats: lo -> bits [0,16), hi -> [16,32).
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
