@@ -67,8 +67,9 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
 #endif
 #ifndef FA_PINGPONG
-#define FA_PINGPONG 0         // 1: the two softmax warpgroups take turns on the exp2 phase (token; measured: no gain,
-                              // passed through named barriers 3/4) instead of contending for MUFU
+#define FA_PINGPONG 0         // experiment knob: 1 = the softmax warpgroups take turns on the exp2 phase,
+                              // 2 = on the whole step (token through named barriers 3/4).  Measured: 1 no
+                              // gain, 2 slower than free-running overlap (profiles/r01_softmax_probe_notes.md)
 #endif
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest

@@ -370,7 +370,11 @@ void run(const char* name, int wgs) {
     run<E, EL, 0, true, true, true>("NOMAX emu" #E "/last" #EL, 1);           \
     run<E, EL, 0, true, true, true>("NOMAX emu" #E "/last" #EL, 2);
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1) {  // single configuration for ncu: production softmax, 1 or 2 warpgroups
+        run<4, 0, 0, true>("emu4/last0 (production)", atoi(argv[1]));
+        return 0;
+    }
     RUN(4, 0, 0, true)
     RUNN(0, 0)
     RUNN(2, 0)
