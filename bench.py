@@ -72,6 +72,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.power_mw = []
         self.reasons = set()
         self.stop_flag = threading.Event()
         self.max_mhz = None
@@ -101,6 +102,7 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power_mw.append(nv.nvmlDeviceGetPowerUsage(self.h))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if mask & bit:
@@ -113,8 +115,11 @@ class ClockSampler(threading.Thread):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(s)}
+        if self.power_mw:
+            out["power_w_max"] = max(self.power_mw) / 1000.0
+        return out
 
 
 def cpu_attention_baseline(shape, dtype_name, reps, warmup=1):
