@@ -71,9 +71,6 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
                               // 2 = on the whole step (token through named barriers 3/4).  Measured: 1 no
                               // gain, 2 slower than free-running overlap (profiles/r01_softmax_probe_notes.md)
 #endif
-#ifndef FA_DEFER_SUM
-#define FA_DEFER_SUM 1        // 1: row sum taken after P is published (off the P-ready critical path)
-#endif
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
 #endif
@@ -503,15 +500,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
-                    if constexpr (FA_DEFER_SUM) {
-                        if (q == 3) exp_fragment_inplace<kBF16, kEmuPairsLast>(sr[q], c2, nm2, pk);
-                        else exp_fragment_inplace<kBF16, kEmuPairs>(sr[q], c2, nm2, pk);
-                    } else {
-                        if (q == 3)
-                            exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
-                        else
-                            exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
-                    }
+                    if (q == 3)
+                        exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    else
+                        exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     tmem_st_32x32b_x16(t_p + q * 16, pk);
                     if (kSplitP && q == 2) {
                         tmem_wait_st();
@@ -531,8 +523,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 if constexpr (kDebug) {
                     if (tr) tr[4] = clk32();
                 }
-                if constexpr (FA_DEFER_SUM) l_run = l_run * alpha + row_sum_128(sr);
-                else l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
+                l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
             }
 
             // ------------------------------- epilogue ------------------------------------

@@ -81,45 +81,4 @@ __device__ __forceinline__ void exp_fragment(const uint32_t (&sr)[32], float2 c2
     }
 }
 
-// Variant of exp_fragment that does NOT accumulate the row sum: p overwrites S in place (fp32 bits)
-// so the sum can be taken later, after P has been published (row_sum_128).  Only the work P depends
-// on (FFMA2, exp2, pack) stays on the path to the MMA warp; the 64 FADD2s run while the warpgroup
-// would otherwise wait for its next S.
-template <bool kBF16, int kEmu>
-__device__ __forceinline__ void exp_fragment_inplace(uint32_t (&sr)[32], float2 c2, float2 nm2,
-                                                     uint32_t (&pk)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float2 x = __ffma2_rn(
-            make_float2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), c2, nm2);
-        float2 p;
-        if (emulate_pair(i, kEmu)) {
-            p = ex2_emulated_x2(x);
-        } else {
-            p.x = ex2_approx(x.x);
-            p.y = ex2_approx(x.y);
-        }
-        sr[2 * i] = __float_as_uint(p.x);
-        sr[2 * i + 1] = __float_as_uint(p.y);
-        pk[i] = pack_16x2<kBF16>(p.x, p.y);
-    }
-}
-
-// fp32 sum of the 128 (un-rounded) P values of a row: 4 independent FADD2 chains.
-__device__ __forceinline__ float row_sum_128(const uint32_t (&sr)[4][32]) {
-    float2 acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        acc[q] = make_float2(__uint_as_float(sr[q][0]), __uint_as_float(sr[q][1]));
-#pragma unroll
-    for (int i = 1; i < 16; ++i) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            acc[q] = __fadd2_rn(acc[q], make_float2(__uint_as_float(sr[q][2 * i]),
-                                                    __uint_as_float(sr[q][2 * i + 1])));
-    }
-    const float2 t = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
-    return t.x + t.y;
-}
-
 }  // namespace fa

@@ -12,12 +12,12 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "defer": {},
-    "nodefer": {"FA_DEFER_SUM": 0},
-    "defer_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
-    "defer_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
-    "defer_emu2": {"FA_EMU_PAIRS": 2},
-    "defer_emu6": {"FA_EMU_PAIRS": 6},
+    "nomax": {},
+    "max": {"FA_NOMAX": 0},
+    "nomax_emu0": {"FA_EMU_PAIRS": 0},
+    "nomax_emu2": {"FA_EMU_PAIRS": 2},
+    "nomax_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "nomax_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
 }
 
 
