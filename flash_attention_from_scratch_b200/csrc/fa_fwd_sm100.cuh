@@ -53,7 +53,7 @@ constexpr int kSmemQ = 0;                                       // Q_0, Q_1
 constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;         // K/V ring
 constexpr int kSmemStage = kSmemKV + kKVStages * kTileBytes;    // O staging: 16 KiB per Q tile
 constexpr int kSmemBar = kSmemStage + kQStages * kHalfBytes;
-constexpr int kNumBarriers = 4 + 2 * kKVStages + 10;
+constexpr int kNumBarriers = 4 + 2 * kKVStages + 13;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
 constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack for manual 1024 B alignment
@@ -88,6 +88,26 @@ static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
+#ifndef FA_SHARED_S
+#define FA_SHARED_S 1         // 1: generation 6 (one S accumulator shared by both Q tiles, P in its own
+                              //    columns, S_s(j+1) issued while softmax_s(j) runs);
+                              // 0: generation 4b (P_s aliases S_s, S_s(j+1) waits for PV_s(j))
+#endif
+constexpr bool kSharedS = FA_SHARED_S != 0;
+static_assert(!kSharedS || kKVStages >= 4, "generation 6 keeps V_j, K_j+1, V_j+1, K_j+2 in flight");
+
+// Tensor-memory column map (512 columns, base 0).
+//   generation 6:  [0,64) P_0   [64,128) P_1   [128,256) S (shared)   [256,384) O_0   [384,512) O_1
+//   generation 4b: [0,128) S_0/P_0   [128,256) S_1/P_1                 [256,384) O_0   [384,512) O_1
+__host__ __device__ constexpr uint32_t tmem_col_s(int s) {
+    return kSharedS ? 128u : static_cast<uint32_t>(s) * 128u;
+}
+__host__ __device__ constexpr uint32_t tmem_col_p(int s) {
+    return kSharedS ? static_cast<uint32_t>(s) * 64u : static_cast<uint32_t>(s) * 128u;
+}
+__host__ __device__ constexpr uint32_t tmem_col_o(int s) {
+    return 256u + static_cast<uint32_t>(s) * 128u;
+}
 
 // Lazy rescale threshold in log2 units: O and l are only rescaled when the running max grows by
 // more than this; until then P is computed against the stale max, i.e. P <= 2^8 (exact in fp32,
@@ -128,9 +148,15 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
               const FwdParams prm, const FwdDebug dbg) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, which makes every
+    // shared-memory address below a link-time constant instead of a live register.
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    uint8_t* smem_gen = smem_raw;
+    if ((smem_base & 1023u) != 0u) {
+        if (threadIdx.x == 0) printf("[fa] dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -147,6 +173,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kKVStages + s); };
     auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kKVStages + s); };
     auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kKVStages + s); };
+    // generation 6 only: S accumulator read out by its softmax warpgroup / PV_s(j) retired
+    const uint32_t s_free = bar0 + 8u * (14 + 2 * kKVStages);
+    auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kKVStages + s); };
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
 
     const int n_blocks = prm.n_kv_blocks;
@@ -182,7 +211,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 mbar_init(p_last(s), 4);
                 mbar_init(o_full(s), 1);
                 mbar_init(o_free(s), 4);
+                mbar_init(pv_done(s), 1);
             }
+            mbar_init(s_free, 4);
             for (int i = 0; i < kKVStages; ++i) {
                 mbar_init(kv_full(i), 1);
                 mbar_init(kv_empty(i), 1);
@@ -276,7 +307,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < kHeadDim / 16; ++k) {
                         const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
-                        umma_ss(tmem_base + s * kBlockN, a0 + off, b0 + off, idesc_qk, k > 0);
+                        umma_ss(tmem_base + tmem_col_s(s), a0 + off, b0 + off, idesc_qk, k > 0);
                     }
                 };
                 auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
@@ -284,9 +315,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         smem_base + kSmemKV + slot * kTileBytes, kHalfBytes, 1024);
 #pragma unroll
                     for (int k = k_begin; k < k_end; ++k) {
-                        umma_ts(tmem_base + 2 * kBlockN + s * kHeadDim,
-                                tmem_base + s * kBlockN + k * 8, b0 + ((k * 2048) >> 4), idesc_pv,
-                                (accumulate || k > 0) ? 1u : 0u);
+                        umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s) + k * 8,
+                                b0 + ((k * 2048) >> 4), idesc_pv, (accumulate || k > 0) ? 1u : 0u);
                     }
                 };
                 auto slot_of = [&](int i) { return i % kKVStages; };
@@ -305,6 +335,110 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         }
                     }
                 }
+                if constexpr (kSharedS) {
+                    // ---------------- generation 6: one shared S accumulator ----------------
+                    // Issue order per work tile (n = n_blocks):
+                    //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
+                    // Every S waits for `s_free` (the other warpgroup has read the previous S out of
+                    // TMEM), every PV_s(j) for P_s(j).  S_s(j+1) is therefore produced while
+                    // softmax_s(j) is still running: the softmax warpgroups never wait for the
+                    // P -> PV -> next S round trip of generation 4b.
+                    int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
+                    uint32_t u = 0;   // S accumulators issued so far (all tiles): s_free parity
+                    uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of s/p/pv barriers
+                    int it = 0;
+                    for (int tile = blockIdx.x; level >= 3 && tile < tile_end;
+                         tile += gridDim.x, ++it) {
+                        auto trace_ptr = [&](int j, int s, int off) -> uint32_t* {
+                            if constexpr (kDebug) {
+                                if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
+                                    j < 32 && lane == 0)
+                                    return reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + off +
+                                           (j * 2 + s) * 4;
+                            }
+                            return nullptr;
+                        };
+                        auto issue_s = [&](int s, int jj) {  // S = Q_s K_jj^T into the shared accumulator
+                            uint32_t* tr = trace_ptr(jj, s, 768);
+                            const int itk = base + 2 * jj;
+                            if constexpr (kDebug) {
+                                if (tr) tr[0] = clk32();
+                            }
+                            mbar_wait(kv_full(slot_of(itk)), parity_of(itk), 200);
+                            if (jj == 0) mbar_wait(q_full(s), (uint32_t)(it & 1), 210 + s);
+                            if (u > 0) mbar_wait(s_free, (u - 1u) & 1u, 270 + s);
+                            if constexpr (kDebug) {
+                                if (tr) tr[1] = clk32();
+                            }
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_qk(s, slot_of(itk));
+                                umma_commit(s_full(s));
+                                if (jj + 1 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
+                                if (s == 1) umma_commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
+                            }
+                            __syncwarp();
+                            if constexpr (kDebug) {
+                                if (tr) tr[2] = clk32();
+                            }
+                            ++u;
+                        };
+                        auto issue_o = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
+                            uint32_t* tr = trace_ptr(j, s, 512);
+                            const int itv = base + 2 * j + 1;
+                            const uint32_t par = (g0 + (uint32_t)j) & 1u;
+                            mbar_wait(kv_full(slot_of(itv)), parity_of(itv), 220);
+                            mbar_wait(p_full(s), par, 230 + s);  // P_s(j) stored, O_s rescaled
+                            if constexpr (kDebug) {
+                                if (tr) tr[0] = clk32();
+                            }
+                            if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
+                                mbar_wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
+                            tc_fence_after();
+                            if constexpr (kSplitP) {
+                                if (elect_one()) issue_pv(s, slot_of(itv), j > 0, 0, 6);
+                                __syncwarp();
+                                if constexpr (kDebug) {
+                                    if (tr) tr[1] = clk32();
+                                }
+                                mbar_wait(p_last(s), par, 250 + s);  // last 32 columns of P_s(j)
+                                if constexpr (kDebug) {
+                                    if (tr) tr[2] = clk32();
+                                }
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    issue_pv(s, slot_of(itv), true, 6, 8);
+                                    umma_commit(pv_done(s));
+                                    if (s == 1) umma_commit(kv_empty(slot_of(itv)));
+                                }
+                                __syncwarp();
+                            } else {
+                                if (elect_one()) {
+                                    issue_pv(s, slot_of(itv), j > 0, 0, 8);
+                                    umma_commit(pv_done(s));
+                                    if (s == 1) umma_commit(kv_empty(slot_of(itv)));
+                                }
+                                __syncwarp();
+                            }
+                            if constexpr (kDebug) {
+                                if (tr) tr[3] = clk32();
+                            }
+                        };
+                        issue_s(0, 0);
+                        issue_s(1, 0);
+                        if (level >= 4) {
+                            if (n_blocks > 1) issue_s(0, 1);
+                            for (int j = 0; j < n_blocks; ++j) {
+                                issue_o(0, j);
+                                if (j + 1 < n_blocks) issue_s(1, j + 1);
+                                issue_o(1, j);
+                                if (j + 2 < n_blocks) issue_s(0, j + 2);
+                            }
+                        }
+                        base += 2 * n_blocks;
+                        g0 += (uint32_t)n_blocks;
+                    }
+                } else {
                 int item = 0;    // K/V ring item counter, same order as the producer
                 uint32_t g = 0;  // KV blocks processed so far (all tiles): parity of s/p barriers
                 int it = 0;
@@ -400,6 +534,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         item += has_next ? 2 : 1;
                     }
                 }
+                }  // generation 4b
             }
         }
         __syncwarp();
@@ -409,9 +544,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const int s = wg;                    // Q tile handled by this warpgroup
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_sel + s * kBlockN;
-        const uint32_t t_p = t_s;
-        const uint32_t t_o = tmem_base + lane_sel + 2 * kBlockN + s * kHeadDim;
+        const uint32_t t_s = tmem_base + lane_sel + tmem_col_s(s);
+        const uint32_t t_p = tmem_base + lane_sel + tmem_col_p(s);
+        const uint32_t t_o = tmem_base + lane_sel + tmem_col_o(s);
         const float c = prm.scale_log2;
         const int kv_tail = prm.seq_len & (kBlockN - 1);  // valid keys in the last block (0 = all)
         uint32_t g = 0;  // KV blocks processed so far (all tiles)
@@ -440,6 +575,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
                 tmem_wait_ld();
+                if constexpr (kSharedS) {
+                    // S is in registers: hand the shared accumulator to the other Q tile's next S
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                }
                 if constexpr (kDebug) {
                     if (tr) tr[1] = clk32();
                 }
@@ -476,7 +617,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                             alpha = ex2_approx(-delta);
                             m_run = mx;
                         }
-                        // O_s is quiescent here: S_s(j) was committed after PV_s(j-1).
+                        // O_s must be quiescent.  Generation 4b: S_s(j) was committed after
+                        // PV_s(j-1); generation 6: wait for PV_s(j-1) explicitly.
+                        if constexpr (kSharedS) {
+                            mbar_wait(pv_done(s), (g - 1u) & 1u, 320 + s);
+                            tc_fence_after();
+                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint32_t o[32];
@@ -504,6 +650,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     else
                         exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
+                    if constexpr (kSharedS) {
+                        // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued ~1.5 softmax
+                        // fragments ago, so this rarely spins)
+                        if (q == 0 && j > 0) {
+                            if constexpr (kDebug) {
+                                if (tr) tr[5] = clk32();
+                            }
+                            mbar_wait(pv_done(s), (g - 1u) & 1u, 330 + s);
+                            tc_fence_after();
+                            if constexpr (kDebug) {
+                                if (tr) tr[6] = clk32();
+                            }
+                        }
+                    }
                     tmem_st_32x32b_x16(t_p + q * 16, pk);
                     if (kSplitP && q == 2) {
                         tmem_wait_st();
@@ -528,7 +688,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
             // ------------------------------- epilogue ------------------------------------
             if (level >= 4) {
-                mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
+                if constexpr (kSharedS) mbar_wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
+                else mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
                 tc_fence_after();
                 const float inv_l = 1.0f / l_run;
                 if constexpr (kDebug) {

@@ -12,12 +12,14 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
     # name: defines
-    "nomax": {},
-    "max": {"FA_NOMAX": 0},
-    "nomax_emu0": {"FA_EMU_PAIRS": 0},
-    "nomax_emu2": {"FA_EMU_PAIRS": 2},
-    "nomax_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
-    "nomax_emu4_4": {"FA_EMU_PAIRS": 4, "FA_EMU_PAIRS_LAST": 4},
+    "g4b": {"FA_SHARED_S": 0},
+    "g6": {},
+    "g6_emu4_4": {"FA_EMU_PAIRS_LAST": 4},
+    "g6_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "g6_emu2": {"FA_EMU_PAIRS": 2},
+    "g6_emu0": {"FA_EMU_PAIRS": 0},
+    "g6_nosplit": {"FA_SPLIT_P": 0},
+    "g6_r200": {"FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 104},
 }
 
 

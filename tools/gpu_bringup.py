@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--H", type=int, default=1)
     ap.add_argument("--knobs", type=int, nargs=8, default=[16, 1024, 16384, 1024, 2048, 0, 8, 4])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bringup.json"))
+    ap.add_argument("--quick", action="store_true", help="fewer shapes after the level ladder")
     args = ap.parse_args()
     if args.one:
         run_one(args)
@@ -188,7 +189,8 @@ def main():
         return 1
     for dtype, B, N, H in [("fp16", 1, 256, 1), ("bf16", 2, 512, 3), ("bf16", 1, 128, 2),
                            ("bf16", 1, 384, 1), ("bf16", 1, 2048, 4), ("fp16", 2, 1024, 16),
-                           ("bf16", 8, 384, 40), ("bf16", 16, 128, 33), ("fp16", 3, 1280, 37)]:
+                           ("bf16", 8, 384, 40), ("bf16", 16, 128, 33), ("fp16", 3, 1280, 37)][
+                               :(3 if args.quick else None)]:
         r3 = spawn(["--dtype", dtype, "--B", B, "--N", N, "--H", H, "--knobs"] + default + [4], env=guard)
         rec(f"shape {dtype} B={B} N={N} H={H}", r3)
     return 0

@@ -38,6 +38,7 @@ def main():
     nb = min(32, N // 128)
     sm = tr[:512].reshape(2, 32, 8)[:, :nb]
     mma = tr[512:768].reshape(32, 2, 4)[:nb]
+    sis = tr[768:1024].reshape(32, 2, 4)[:nb]  # generation 6: S issue (enter, deps met, issued)
     t0 = int(sm[0, 0, 0])
     d = lambda a, b: int((a - b) & 0xFFFFFFFF)  # noqa: E731
     rows = []
@@ -53,14 +54,19 @@ def main():
                 "mma_pfull_lat": d(m[0], e[3]), "mma_pv6_issue": d(m[1], m[0]),
                 "mma_plast_lat": d(m[2], e[4]), "mma_tail_issue": d(m[3], m[2]),
                 "period": d(nxt[0], e[0]),
+                # generation 6 only (zero otherwise): wait for PV_s(j-1) before the first P store,
+                # and the issue of S_s(j): time blocked on K / s_free, S issued -> softmax sees it
+                "pv_wait": d(e[6], e[5]), "s_issue_blocked": d(sis[j, s][1], sis[j, s][0]),
+                "s_issue_to_seen": d(e[0], sis[j, s][2]), "s_issued_at": d(sis[j, s][2], t0),
             }
             rows.append(r)
             print(f"{j:3d} {s}  | {r['t_S']:7d} {r['ld']:5d} {r['max']:6d} {r['exp96']:6d} {r['exp32']:6d} | "
                   f"{r['wait_next_S']:6d} | {r['mma_pfull_lat']:6d} {r['mma_pv6_issue']:6d} "
-                  f"{r['mma_plast_lat']:6d} {r['mma_tail_issue']:6d} | period {r['period']}")
+                  f"{r['mma_plast_lat']:6d} {r['mma_tail_issue']:6d} | period {r['period']} | pvwait {r['pv_wait']} "
+                  f"s_blocked {r['s_issue_blocked']} s_issue->seen {r['s_issue_to_seen']}")
     import statistics as st
     keys = ["ld", "max", "exp96", "exp32", "wait_next_S", "mma_pfull_lat", "mma_pv6_issue", "mma_plast_lat",
-            "mma_tail_issue", "period"]
+            "mma_tail_issue", "period", "pv_wait", "s_issue_blocked", "s_issue_to_seen"]
     summ = {k_: st.median(r[k_] for r in rows if r["j"] >= 4) for k_ in keys}
     print("MEDIANS", json.dumps(summ))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
