@@ -29,6 +29,7 @@ SYMBOLS = {
     "fa_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
     "fa_launch_count": (_L, []),
+    "fa_set_kernel_mode": (_I, [_I]),
     "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32), _P]),
 }
 
@@ -63,6 +64,17 @@ def last_error() -> str:
 
 def launch_count() -> int:
     return int(load().fa_launch_count())
+
+
+MODE_AUTO, MODE_SINGLE, MODE_PAIR = 0, 1, 2
+
+
+def set_kernel_mode(mode: int) -> int:
+    """Select the machine mapping (include/fa_sm100.h: fa_set_kernel_mode); returns the previous one."""
+    prev = int(load().fa_set_kernel_mode(int(mode)))
+    if prev < 0:
+        raise ValueError(f"invalid kernel mode {mode}")
+    return prev
 
 
 def kernel_info() -> dict:

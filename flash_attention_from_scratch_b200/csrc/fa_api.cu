@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -72,8 +73,27 @@ DeviceState g_dev[kMaxDevices];
 
 template <bool kBF16, bool kDebug, bool kRagged>
 cudaError_t set_smem_attr() {
-    return cudaFuncSetAttribute(fa::fa_fwd_kernel<kBF16, kDebug, kRagged>,
+    cudaError_t e = cudaFuncSetAttribute(fa::fa_fwd_kernel<kBF16, kDebug, kRagged>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         fa::kSmemLaunchBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fa::fa_fwd_kernel_pair<kBF16, kDebug, kRagged>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
+}
+
+// Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  CTA pairs (generation 7) cover 512
+// query rows per work tile, so AUTO uses them when seq_len > 256.
+std::atomic<int> g_mode{[] {
+    const char* m = getenv("FA_SM100_MODE");
+    if (m != nullptr && strcmp(m, "single") == 0) return FA_MODE_SINGLE;
+    if (m != nullptr && strcmp(m, "pair") == 0) return FA_MODE_PAIR;
+    return FA_MODE_AUTO;
+}()};
+bool use_pair_kernel(int seq_len) {
+    const int mode = g_mode.load(std::memory_order_relaxed);
+    if (mode == FA_MODE_SINGLE) return false;
+    if (mode == FA_MODE_PAIR) return true;
+    return seq_len > fa::kQStages * fa::kBlockM;
 }
 
 // One-time per-device setup: capability check + opt-in dynamic shared memory
@@ -135,13 +155,13 @@ struct Problem {
 
 // (d, H, N, B) view with a {64, 1, 128, 1} box and 128-byte swizzle: one box = 128 rows of 128 B,
 // the layout both the tcgen05 smem descriptors and the epilogue assume.
-int make_tensor_map(CUtensorMap* out, const void* ptr, const Problem& p) {
+int make_tensor_map(CUtensorMap* out, const void* ptr, const Problem& p, int box_rows = 128) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA_ERR_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
     const cuuint64_t dims[4] = {128, (cuuint64_t)p.H, (cuuint64_t)p.N, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.sh * 2, (cuuint64_t)p.sn * 2,
                                    (cuuint64_t)p.sb * 2};
-    const cuuint32_t box[4] = {64, 1, 128, 1};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = (p.dtype == FA_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -182,9 +202,12 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     int rc = init_device(dev);
     if (rc != FA_OK) return rc;
 
+    const bool pair = use_pair_kernel(p.N);
+    const int rows_per_tile = (pair ? 2 : 1) * fa::kQStages * fa::kBlockM;
     CUtensorMap tq, tk, tv, to;
     if ((rc = make_tensor_map(&tq, p.q, p)) != FA_OK) return rc;
-    if ((rc = make_tensor_map(&tk, p.k, p)) != FA_OK) return rc;
+    // a CTA of a pair loads 64 keys of every K block
+    if ((rc = make_tensor_map(&tk, p.k, p, pair ? 64 : 128)) != FA_OK) return rc;
     if ((rc = make_tensor_map(&tv, p.v, p)) != FA_OK) return rc;
     if ((rc = make_tensor_map(&to, p.o, p)) != FA_OK) return rc;
 
@@ -193,19 +216,29 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     prm.seq_len = p.N;
     prm.n_heads = p.H;
     prm.n_kv_blocks = (p.N + fa::kBlockN - 1) / fa::kBlockN;
-    prm.n_q_pairs = (p.N + fa::kQStages * fa::kBlockM - 1) / (fa::kQStages * fa::kBlockM);
+    prm.n_q_groups = (p.N + rows_per_tile - 1) / rows_per_tile;
     prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
 
-    const long long n_tiles = 1LL * p.B * p.H * prm.n_q_pairs;
+    const long long n_tiles = 1LL * p.B * p.H * prm.n_q_groups;
     if (n_tiles > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld tiles", n_tiles);
     prm.n_tiles = static_cast<int>(n_tiles);
     // persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
-    dim3 grid((unsigned)(n_tiles < n_sms ? n_tiles : n_sms)), block(fa::kNumThreads);
+    const long long n_workers = pair ? n_sms / 2 : n_sms;  // CTAs, or CTA pairs (one cluster per TPC)
+    const unsigned n_active = (unsigned)(n_tiles < n_workers ? n_tiles : n_workers);
+    dim3 grid(pair ? 2 * n_active : n_active), block(fa::kNumThreads);
     // one instantiation per (dtype, ragged tail?); the debug build always carries the masking code
     const bool ragged = kDebug || (p.N % fa::kBlockN) != 0;
     auto go = [&](auto kern) { kern<<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg); };
-    if (p.dtype == FA_DTYPE_BF16) {
+    if (pair) {
+        if (p.dtype == FA_DTYPE_BF16) {
+            if (ragged) go(fa::fa_fwd_kernel_pair<true, kDebug, true>);
+            else go(fa::fa_fwd_kernel_pair<true, false, false>);
+        } else {
+            if (ragged) go(fa::fa_fwd_kernel_pair<false, kDebug, true>);
+            else go(fa::fa_fwd_kernel_pair<false, false, false>);
+        }
+    } else if (p.dtype == FA_DTYPE_BF16) {
         if (ragged) go(fa::fa_fwd_kernel<true, kDebug, true>);
         else go(fa::fa_fwd_kernel<true, false, false>);
     } else {
@@ -244,6 +277,11 @@ extern "C" {
 const char* fa_last_error_string(void) { return g_err; }
 
 int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fa_set_kernel_mode(int mode) {
+    if (mode != FA_MODE_AUTO && mode != FA_MODE_SINGLE && mode != FA_MODE_PAIR) return -1;
+    return g_mode.exchange(mode, std::memory_order_relaxed);
+}
 
 int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_capability) {
     cudaDeviceProp prop;

@@ -8,23 +8,31 @@
 //     l += rowsum(P) (un-rounded fp32);  O += rn16(P) V (fp32 accumulate);  out = rn16(O / l)
 // but a different machine mapping -- nothing of the mma.sync / ldmatrix / cp.async path is kept:
 //
-//   * PERSISTENT: one CTA per SM walks a static list of work tiles (tile = 2 Q tiles of 128 rows =
-//     256 query rows of one (batch, head); consecutive tiles share K/V in L2).  Loads, MMAs and
-//     the epilogue of neighbouring tiles overlap: the TMA producer and the MMA issuer run ahead
-//     into the next tile while the softmax warpgroups finish the current one.
+//   * PERSISTENT: every CTA walks a static list of work tiles.  A CTA owns 2 Q tiles of 128 rows
+//     (256 query rows of one (batch, head)); consecutive tiles share K/V in L2.  Loads, MMAs and the
+//     epilogue of neighbouring tiles overlap.
 //   * TMA (cp.async.bulk.tensor, 128B swizzle) stages Q tiles and K/V blocks through shared
-//     memory guarded by full/empty mbarriers (K/V: ring of 4 x 32 KiB slots).
+//     memory guarded by full/empty mbarriers.
 //   * one thread issues tcgen05.mma: S_s = Q_s K_j^T (operands from smem) and O_s += P_s V_j
-//     (P read from tensor memory, V from smem, MN-major); accumulators in TMEM:
-//       columns [0,128) S_0 / P_0, [128,256) S_1 / P_1, [256,384) O_0, [384,512) O_1
+//     (P read from tensor memory, V from smem, MN-major); accumulators in tensor memory.
 //   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
 //     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit in two
 //     parts (96 + 32 columns) so PV starts early, lazy rescale of O (only when the row max grew
 //     by more than 2^8), final 1/l scaling and TMA store of O through swizzled shared memory.
-//   The two Q tiles ping-pong: while the tensor core runs PV_1(j-1) and S_1(j) the softmax
-//   warpgroup 0 works on S_0(j), and vice versa.
 //
-// Generations 1-3 and the measurements that led here: profiles/r01_*_notes.md.
+// Three protocols live in this file (profiles/r01_*_notes.md has the measurements behind each):
+//   generation 4b (FA_SHARED_S=0): P_s aliases S_s; S_s(j+1) is issued behind PV_s(j).
+//   generation 6  (FA_SHARED_S=1): ONE S accumulator shared by both Q tiles, P_s in its own
+//       columns; S_s(j+1) is issued as soon as the other warpgroup has read the previous S out
+//       of TMEM, i.e. while softmax_s(j) is still running.
+//   generation 7  (kPair, built on 6): two CTAs of a cluster form a tcgen05 `cta_group::2` pair.
+//       The even CTA's MMA warp issues M = 256 MMAs for both; each CTA keeps its own Q tiles,
+//       softmax and epilogue but loads only HALF of every K block (64 keys) and V block (64 of
+//       the 128 d columns): per MMA a CTA reads 6 KiB of smem operands instead of 8, and TMA
+//       writes half as much.  Reason: tools/mma_probe.cu shows an isolated 128x128x16 SS MMA runs
+//       at the nominal 64 clk, but at 128 B/clk it needs ALL of the shared-memory bandwidth, and
+//       in the attention loop (TMA writes of K/V arriving at the same time) the cycle trace showed
+//       ~100 clk per QK^T MMA: shared-memory bandwidth, not the tensor core, paced generation 4b/6.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -39,11 +47,12 @@ namespace fa {
 constexpr int kBlockM = 128;   // query rows per Q tile == TMEM lanes
 constexpr int kBlockN = 128;   // key/value rows per block
 constexpr int kHeadDim = 128;  // d_head (the only one the reference supports, README.md:9-15)
-constexpr int kQStages = 2;    // Q tiles per work tile
+constexpr int kQStages = 2;    // Q tiles per CTA
 #ifndef FA_KV_STAGES
 #define FA_KV_STAGES 4
 #endif
-constexpr int kKVStages = FA_KV_STAGES;  // K/V ring slots (each slot holds one K block or one V block)
+constexpr int kKVStages = FA_KV_STAGES;  // K/V ring slots of 32 KiB (a CTA pair uses 2x as many 16 KiB slots)
+constexpr int kMaxStages = 2 * kKVStages;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
 constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
@@ -53,10 +62,10 @@ constexpr int kSmemQ = 0;                                       // Q_0, Q_1
 constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;         // K/V ring
 constexpr int kSmemStage = kSmemKV + kKVStages * kTileBytes;    // O staging: 16 KiB per Q tile
 constexpr int kSmemBar = kSmemStage + kQStages * kHalfBytes;
-constexpr int kNumBarriers = 4 + 2 * kKVStages + 13;
+constexpr int kNumBarriers = 4 + 2 * kMaxStages + 13;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
-constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack for manual 1024 B alignment
+constexpr int kSmemLaunchBytes = kSmemTotal + 1024;  // slack (the base is 1024-byte aligned by declaration)
 static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared memory of sm_100");
 
 // Tunables (overridable with -D at build time; tools/build_variants.py sweeps them).
@@ -64,12 +73,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_EMU_PAIRS 4        // of every 16 (p0,p1) pairs, how many use the FMA-pipe exp2 (rest: MUFU)
 #endif
 #ifndef FA_EMU_PAIRS_LAST
-#define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment (on the critical path)
-#endif
-#ifndef FA_PINGPONG
-#define FA_PINGPONG 0         // experiment knob: 1 = the softmax warpgroups take turns on the exp2 phase,
-                              // 2 = on the whole step (token through named barriers 3/4).  Measured: 1 no
-                              // gain, 2 slower than free-running overlap (profiles/r01_softmax_probe_notes.md)
+#define FA_EMU_PAIRS_LAST 0   // same for the last 32-column fragment
 #endif
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
@@ -83,25 +87,24 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
 constexpr bool kSplitP = FA_SPLIT_P != 0;
-constexpr bool kPingPong = FA_PINGPONG != 0;
 static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
 #ifndef FA_SHARED_S
-#define FA_SHARED_S 1         // 1: generation 6 (one S accumulator shared by both Q tiles, P in its own
-                              //    columns, S_s(j+1) issued while softmax_s(j) runs);
-                              // 0: generation 4b (P_s aliases S_s, S_s(j+1) waits for PV_s(j))
+#define FA_SHARED_S 1         // single-CTA kernel: 1 = generation 6, 0 = generation 4b (see top of file)
 #endif
-constexpr bool kSharedS = FA_SHARED_S != 0;
-static_assert(!kSharedS || kKVStages >= 4, "generation 6 keeps V_j, K_j+1, V_j+1, K_j+2 in flight");
+constexpr bool kSharedSDefault = FA_SHARED_S != 0;
+static_assert(kKVStages >= 4, "generation 6/7 keep V_j, K_j+1, V_j+1, K_j+2 in flight");
 
 // Tensor-memory column map (512 columns, base 0).
-//   generation 6:  [0,64) P_0   [64,128) P_1   [128,256) S (shared)   [256,384) O_0   [384,512) O_1
-//   generation 4b: [0,128) S_0/P_0   [128,256) S_1/P_1                 [256,384) O_0   [384,512) O_1
+//   generation 6/7: [0,64) P_0   [64,128) P_1   [128,256) S (shared)   [256,384) O_0   [384,512) O_1
+//   generation 4b:  [0,128) S_0/P_0   [128,256) S_1/P_1                 [256,384) O_0   [384,512) O_1
+template <bool kSharedS>
 __host__ __device__ constexpr uint32_t tmem_col_s(int s) {
     return kSharedS ? 128u : static_cast<uint32_t>(s) * 128u;
 }
+template <bool kSharedS>
 __host__ __device__ constexpr uint32_t tmem_col_p(int s) {
     return kSharedS ? static_cast<uint32_t>(s) * 64u : static_cast<uint32_t>(s) * 128u;
 }
@@ -116,11 +119,12 @@ constexpr float kRescaleThreshold = 8.0f;
 
 // Bring-up hooks (only read by the kDebug instantiation; see tools/gpu_bringup.py).
 struct FwdDebug {
-    float* dump;      // level 2: raw smem Q_0 | K_0 (2 x 8192 words); level >= 3: S(block 0)
-                      // [2][128][128] of work tile 0, then l [2][128], m [2][128]
+    float* dump;      // level 2: raw smem Q_0 | first 32 KiB of the K/V ring (2 x 8192 words);
+                      // level >= 3: S(block 0) [2][128][128] of work tile 0, then l [2][128], m [2][128]
     uint32_t level;   // 1: setup/teardown only, 2: + TMA Q_0,K_0, 3: + S = QK^T, >= 4: everything,
                       // 5: everything + cycle trace of CTA 0 / tile 0 (words from kTraceBase on:
-                      // softmax [stage][block<32][8 events], then MMA [block<32][stage][4 events])
+                      // softmax [stage][block<32][8 events], PV issue [block<32][stage][4 events],
+                      // S issue [block<32][stage][4 events])
     uint32_t* diag;   // host-mapped diagnostics ring (hang-guard builds)
 };
 
@@ -136,18 +140,25 @@ struct FwdParams {
     int seq_len;
     int n_heads;
     int n_kv_blocks;   // ceil(seq_len / 128); keys beyond seq_len in the last block are masked
-    int n_q_pairs;     // ceil(seq_len / 256): work tiles per (batch, head)
-    int n_tiles;       // batch * n_heads * n_q_pairs
+    int n_q_groups;    // work tiles per (batch, head): ceil(seq_len / 256), CTA pairs: ceil(seq_len / 512)
+    int n_tiles;       // batch * n_heads * n_q_groups
     float scale_log2;  // log2(e) / sqrt(d_head)
 };
 
 // kRagged: seq_len % 128 != 0 (tail keys masked); a separate instantiation because the masking
 // code costs 1.6 % at the headline even when never taken (profiles/r01_sweep9_ragged_ab.json).
-template <bool kBF16, bool kDebug, bool kRagged>
-__global__ void __launch_bounds__(kNumThreads, 1)
-fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-              const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-              const FwdParams prm, const FwdDebug dbg) {
+// kPair: generation 7 (the kernel is then launched with cluster dimension 2).
+template <bool kBF16, bool kDebug, bool kRagged, bool kPair>
+__device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUtensorMap& tm_k,
+                                            const CUtensorMap& tm_v, const CUtensorMap& tm_o,
+                                            const FwdParams& prm, const FwdDebug& dbg) {
+    constexpr bool kSharedS = kPair || kSharedSDefault;
+    constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;      // K/V ring slots ...
+    constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
+    constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
+    constexpr uint32_t kArrivals = kPair ? 8u : 4u;  // softmax warps arriving on one barrier
+    constexpr int kRowsPerTile = (kPair ? 2 : 1) * kQStages * kBlockM;
+
     // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, which makes every
     // shared-memory address below a link-time constant instead of a live register.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,36 +172,53 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int wg = warp >> 2;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;  // CTA inside its pair
+    const bool is_leader = rank == 0;                       // the CTA whose MMA warp issues
+    const int cta_lin = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_cta = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-    // barrier addresses
+    // Barriers.  Every CTA holds a full set at the same offsets.  In a pair:
+    //   * q_full / kv_full / p_full / p_last / o_free / s_free are used in the LEADER's copy only
+    //     (TMA of both CTAs credits its bytes there; softmax warps of the peer arrive remotely);
+    //   * q_empty / kv_empty / s_full / pv_done are signalled in BOTH copies by one multicast
+    //     tcgen05.commit and waited on locally.
     const uint32_t bar0 = smem_base + kSmemBar;
     auto q_full = [&](int s) { return bar0 + 8u * s; };
     auto q_empty = [&](int s) { return bar0 + 8u * (2 + s); };
     auto kv_full = [&](int i) { return bar0 + 8u * (4 + i); };
-    auto kv_empty = [&](int i) { return bar0 + 8u * (4 + kKVStages + i); };
-    auto s_full = [&](int s) { return bar0 + 8u * (4 + 2 * kKVStages + s); };
-    auto p_full = [&](int s) { return bar0 + 8u * (6 + 2 * kKVStages + s); };
-    auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kKVStages + s); };
-    auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kKVStages + s); };
-    auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kKVStages + s); };
-    // generation 6 only: S accumulator read out by its softmax warpgroup / PV_s(j) retired
-    const uint32_t s_free = bar0 + 8u * (14 + 2 * kKVStages);
-    auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kKVStages + s); };
+    auto kv_empty = [&](int i) { return bar0 + 8u * (4 + kMaxStages + i); };
+    auto s_full = [&](int s) { return bar0 + 8u * (4 + 2 * kMaxStages + s); };
+    auto p_full = [&](int s) { return bar0 + 8u * (6 + 2 * kMaxStages + s); };
+    auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kMaxStages + s); };
+    auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kMaxStages + s); };  // generation 4b only
+    auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kMaxStages + s); };
+    const uint32_t s_free = bar0 + 8u * (14 + 2 * kMaxStages);                   // generation 6/7
+    auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kMaxStages + s); };  // generation 6/7
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
+
+    auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait<kPair>(bar, parity, tag); };
+    auto arrive_leader = [&](uint32_t bar) {  // one arrival on the leader CTA's copy of `bar`
+        if constexpr (kPair) mbar_arrive_cluster(mapa_shared(bar, 0));
+        else mbar_arrive(bar);
+    };
+    auto commit = [&](uint32_t bar) {  // all earlier MMAs retired -> arrive (pair: in both CTAs)
+        if constexpr (kPair) umma_commit_2cta(bar, 3);
+        else umma_commit(bar);
+    };
 
     const int n_blocks = prm.n_kv_blocks;
     const uint32_t level = kDebug ? dbg.level : 4u;
-    // work tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (q-pair index fastest so
-    // the CTAs running at the same time share the K/V of a few (batch, head) pairs in L2)
-    const int tile_end = (kDebug && level < 4) ? min(prm.n_tiles, (int)blockIdx.x + 1) : prm.n_tiles;
+    // work tiles of this CTA (pair): cta_lin, cta_lin + n_cta, ...  (q-group index fastest so the
+    // CTAs running at the same time share the K/V of a few (batch, head) pairs in L2)
+    const int tile_end = (kDebug && level < 4) ? min(prm.n_tiles, cta_lin + 1) : prm.n_tiles;
     struct TileCoord {
         int q_row0, head, batch;
     };
     auto coord_of = [&](int tile) {
         TileCoord tc;
-        const int qpair = tile % prm.n_q_pairs;
-        const int bh = tile / prm.n_q_pairs;
-        tc.q_row0 = qpair * (kQStages * kBlockM);
+        const int qgroup = tile % prm.n_q_groups;
+        const int bh = tile / prm.n_q_groups;
+        tc.q_row0 = qgroup * kRowsPerTile + (int)rank * (kQStages * kBlockM);
         tc.head = bh % prm.n_heads;
         tc.batch = bh / prm.n_heads;
         return tc;
@@ -207,22 +235,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 mbar_init(q_full(s), 1);
                 mbar_init(q_empty(s), 1);
                 mbar_init(s_full(s), 1);
-                mbar_init(p_full(s), 4);  // one elected arrive per softmax warp
-                mbar_init(p_last(s), 4);
+                mbar_init(p_full(s), kArrivals);  // one elected arrive per softmax warp
+                mbar_init(p_last(s), kArrivals);
                 mbar_init(o_full(s), 1);
-                mbar_init(o_free(s), 4);
+                mbar_init(o_free(s), kArrivals);
                 mbar_init(pv_done(s), 1);
             }
-            mbar_init(s_free, 4);
-            for (int i = 0; i < kKVStages; ++i) {
+            mbar_init(s_free, kArrivals);
+            for (int i = 0; i < kStages; ++i) {
                 mbar_init(kv_full(i), 1);
                 mbar_init(kv_empty(i), 1);
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_ptr_smem, kTmemCols);
-        tmem_relinquish();
+        if constexpr (kPair) {
+            tmem_alloc_2cta(tmem_ptr_smem, kTmemCols);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(tmem_ptr_smem, kTmemCols);
+            tmem_relinquish();
+        }
     } else if (warp == 9 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
@@ -230,7 +263,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         tma_prefetch_desc(&tm_o);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync();  // the peer's barriers exist before anything targets them
+    else __syncthreads();
     tc_fence_after();
     // All 512 TMEM columns are allocated by the only CTA on this SM, so the base address is 0.
     // Using the literal keeps every tcgen05 operand warp-uniform (no R2UR per MMA).
@@ -245,225 +279,250 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (warp == 9) {
             // ================================ TMA producer ================================
             // Convergent warp, one elected lane issues the copies (same reason as the MMA warp).
-            {
-                int item = 0;  // K/V ring item counter (runs across tiles): K0, V0, K1, V1, ...
-                int it = 0;    // local tile counter
-                for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
-                    const TileCoord tc = coord_of(tile);
-                    auto load_tile = [&](const CUtensorMap* map, uint32_t dst, uint32_t bar, int row0) {
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(bar, kTileBytes);
-                            tma_load_4d(dst, map, bar, 0, tc.head, row0, tc.batch);
-                            tma_load_4d(dst + kHalfBytes, map, bar, 64, tc.head, row0, tc.batch);
-                        }
-                        __syncwarp();
-                    };
-                    auto load_q = [&](int s) {
-                        // Q_s smem is free once the previous tile's last S_s MMA retired
-                        mbar_wait(q_empty(s), (uint32_t)((it & 1) ^ 1), 110 + s);
-                        load_tile(&tm_q, smem_base + kSmemQ + s * kTileBytes, q_full(s),
-                                  tc.q_row0 + s * kBlockM);
-                    };
-                    auto load_kv = [&](const CUtensorMap* map, int blk) {
-                        const int slot = item % kKVStages;
-                        const uint32_t use = item / kKVStages;
-                        mbar_wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
-                        load_tile(map, smem_base + kSmemKV + slot * kTileBytes, kv_full(slot),
-                                  blk * kBlockN);
-                        ++item;
-                    };
-                    if (level >= 2) {
-                        load_q(0);
-                        load_kv(&tm_k, 0);
+            // In a pair every CTA loads its own Q tiles, keys [64 rank, 64 rank + 64) of each K
+            // block and d columns [64 rank, 64 rank + 64) of each V block; all bytes are credited to
+            // the leader's full barrier, on which only the leader posts the expected total.
+            int item = 0;  // K/V ring item counter (runs across tiles): K0, V0, K1, V1, ...
+            int it = 0;    // local tile counter
+            for (int tile = cta_lin; tile < tile_end; tile += n_cta, ++it) {
+                const TileCoord tc = coord_of(tile);
+                auto load_box = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int row0) {
+                    if constexpr (kPair)
+                        tma_load_4d_2cta(dst, map, mapa_shared(bar, 0), c0, tc.head, row0, tc.batch);
+                    else
+                        tma_load_4d(dst, map, bar, c0, tc.head, row0, tc.batch);
+                };
+                auto load_q = [&](int s) {
+                    // Q_s smem is free once the previous tile's last S_s MMA retired
+                    wait(q_empty(s), (uint32_t)((it & 1) ^ 1), 110 + s);
+                    if (elect_one()) {
+                        const uint32_t dst = smem_base + kSmemQ + s * kTileBytes;
+                        const int row0 = tc.q_row0 + s * kBlockM;
+                        if (is_leader) mbar_arrive_expect_tx(q_full(s), (kPair ? 2 : 1) * kTileBytes);
+                        load_box(dst, &tm_q, q_full(s), 0, row0);
+                        load_box(dst + kHalfBytes, &tm_q, q_full(s), 64, row0);
                     }
-                    if (level >= 3) load_q(1);
-                    if (level >= 4) {
-                        load_kv(&tm_v, 0);
-                        for (int j = 1; j < n_blocks; ++j) {
-                            load_kv(&tm_k, j);
-                            load_kv(&tm_v, j);
+                    __syncwarp();
+                };
+                auto load_kv = [&](bool is_k, int blk) {
+                    const int slot = item % kStages;
+                    const uint32_t use = item / kStages;
+                    wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
+                    if (elect_one()) {
+                        const uint32_t dst = smem_base + kSmemKV + slot * kSlotBytes;
+                        if (is_leader) mbar_arrive_expect_tx(kv_full(slot), kTileBytes);
+                        if (kPair && !is_k) {  // V: one box, this CTA's 64 d columns of all 128 keys
+                            load_box(dst, &tm_v, kv_full(slot), 64 * (int)rank, blk * kBlockN);
+                        } else {  // K (pair: this CTA's 64 keys; tm_k then has a 64-row box), or K / V whole
+                            const CUtensorMap* map = is_k ? &tm_k : &tm_v;
+                            const int row0 = blk * kBlockN + (kPair ? 64 * (int)rank : 0);
+                            load_box(dst, map, kv_full(slot), 0, row0);
+                            load_box(dst + kKHalfBytes, map, kv_full(slot), 64, row0);
                         }
+                    }
+                    __syncwarp();
+                    ++item;
+                };
+                if (level >= 2) {
+                    load_q(0);
+                    load_kv(true, 0);
+                }
+                if (level >= 3) load_q(1);
+                if (level >= 4) {
+                    load_kv(false, 0);
+                    for (int j = 1; j < n_blocks; ++j) {
+                        load_kv(true, j);
+                        load_kv(false, j);
                     }
                 }
             }
-        } else if (warp == 8) {
+        } else if (warp == 8 && is_leader) {
             // ================================ MMA issuer ==================================
             // The whole warp runs this loop CONVERGENTLY (all lanes poll the barriers) and one
             // elected lane issues the tcgen05 instructions.  Issuing from a `lane == 0` divergent
             // branch made ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY serialisation loop with
             // three R2URs: ~90 cycles per MMA, more than the 64 cycles the MMA takes to execute
             // (profiles/r01_v4_trace_notes.md).
-            {
-                constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, kBlockM, kBlockN, false);
-                constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kBlockM, kHeadDim, true);
-                // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
-                // V tiles: MN-major; next 64-wide d chunk 16 KiB away (LBO), next 8 kv rows 1 KiB
-                // (SBO); one k-step = 16 kv rows = 2 KiB.  P (A operand in TMEM): 8 columns/k-step.
-                auto issue_qk = [&](int s, int slot) {
-                    const uint64_t a0 =
-                        umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, 16, 1024);
-                    const uint64_t b0 =
-                        umma_smem_desc_sw128(smem_base + kSmemKV + slot * kTileBytes, 16, 1024);
+            constexpr int kM = kPair ? 2 * kBlockM : kBlockM;
+            constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, kM, kBlockN, false);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kM, kHeadDim, true);
+            // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
+            // V tiles: MN-major; next 64-wide d chunk 16 KiB away (LBO), next 8 kv rows 1 KiB
+            // (SBO); one k-step = 16 kv rows = 2 KiB.  P (A operand in TMEM): 8 columns/k-step.
+            // Pair: the B descriptors cover this CTA's half (64 keys of K / 64 d columns of V);
+            // the peer CTA's tensor core reads the same offsets of its own shared memory.
+            auto issue_qk = [&](int s, int slot) {
+                const uint64_t a0 = umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, 16, 1024);
+                const uint64_t b0 =
+                    umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < kHeadDim / 16; ++k) {
-                        const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
-                        umma_ss(tmem_base + tmem_col_s(s), a0 + off, b0 + off, idesc_qk, k > 0);
-                    }
-                };
-                auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
-                    const uint64_t b0 = umma_smem_desc_sw128(
-                        smem_base + kSmemKV + slot * kTileBytes, kHalfBytes, 1024);
+                for (int k = 0; k < kHeadDim / 16; ++k) {
+                    const uint32_t a_off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
+                    const uint32_t b_off = ((k >> 2) * kKHalfBytes + (k & 3) * 32) >> 4;
+                    if constexpr (kPair)
+                        umma_ss_2cta(tmem_base + tmem_col_s<kSharedS>(s), a0 + a_off, b0 + b_off, idesc_qk, k > 0);
+                    else
+                        umma_ss(tmem_base + tmem_col_s<kSharedS>(s), a0 + a_off, b0 + b_off, idesc_qk, k > 0);
+                }
+            };
+            auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
+                const uint64_t b0 = umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes,
+                                                         kHalfBytes, 1024);
 #pragma unroll
-                    for (int k = k_begin; k < k_end; ++k) {
-                        umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s) + k * 8,
-                                b0 + ((k * 2048) >> 4), idesc_pv, (accumulate || k > 0) ? 1u : 0u);
-                    }
-                };
-                auto slot_of = [&](int i) { return i % kKVStages; };
-                auto parity_of = [&](int i) { return (uint32_t)((i / kKVStages) & 1); };
+                for (int k = k_begin; k < k_end; ++k) {
+                    const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
+                    if constexpr (kPair)
+                        umma_ts_2cta(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                     b0 + ((k * 2048) >> 4), idesc_pv, acc);
+                    else
+                        umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                b0 + ((k * 2048) >> 4), idesc_pv, acc);
+                }
+            };
+            auto slot_of = [&](int i) { return i % kStages; };
+            auto parity_of = [&](int i) { return (uint32_t)((i / kStages) & 1); };
 
-                if constexpr (kDebug) {
-                    if (level == 2) {  // raw smem images of Q_0 and K_0 as TMA wrote them
-                        mbar_wait(kv_full(0), 0, 200);
-                        mbar_wait(q_full(0), 0, 210);
-                        if (lane == 0 && dbg.dump != nullptr && blockIdx.x == 0) {
-                            const uint32_t* qs = reinterpret_cast<const uint32_t*>(smem_gen + kSmemQ);
-                            const uint32_t* ks = reinterpret_cast<const uint32_t*>(smem_gen + kSmemKV);
-                            uint32_t* out = reinterpret_cast<uint32_t*>(dbg.dump);
-                            for (int i = 0; i < kTileBytes / 4; ++i) out[i] = qs[i];
-                            for (int i = 0; i < kTileBytes / 4; ++i) out[kTileBytes / 4 + i] = ks[i];
-                        }
+            if constexpr (kDebug) {
+                if (level == 2) {  // raw smem images of Q_0 and K_0 as TMA wrote them
+                    wait(kv_full(0), 0, 200);
+                    wait(q_full(0), 0, 210);
+                    if (lane == 0 && dbg.dump != nullptr && blockIdx.x == 0) {
+                        const uint32_t* qs = reinterpret_cast<const uint32_t*>(smem_gen + kSmemQ);
+                        const uint32_t* ks = reinterpret_cast<const uint32_t*>(smem_gen + kSmemKV);
+                        uint32_t* out = reinterpret_cast<uint32_t*>(dbg.dump);
+                        for (int i = 0; i < kTileBytes / 4; ++i) out[i] = qs[i];
+                        for (int i = 0; i < kTileBytes / 4; ++i) out[kTileBytes / 4 + i] = ks[i];
                     }
                 }
-                if constexpr (kSharedS) {
-                    // ---------------- generation 6: one shared S accumulator ----------------
-                    // Issue order per work tile (n = n_blocks):
-                    //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
-                    // Every S waits for `s_free` (the other warpgroup has read the previous S out of
-                    // TMEM), every PV_s(j) for P_s(j).  S_s(j+1) is therefore produced while
-                    // softmax_s(j) is still running: the softmax warpgroups never wait for the
-                    // P -> PV -> next S round trip of generation 4b.
-                    int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
-                    uint32_t u = 0;   // S accumulators issued so far (all tiles): s_free parity
-                    uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of s/p/pv barriers
-                    int it = 0;
-                    for (int tile = blockIdx.x; level >= 3 && tile < tile_end;
-                         tile += gridDim.x, ++it) {
-                        auto trace_ptr = [&](int j, int s, int off) -> uint32_t* {
-                            if constexpr (kDebug) {
-                                if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
-                                    j < 32 && lane == 0)
-                                    return reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + off +
-                                           (j * 2 + s) * 4;
-                            }
-                            return nullptr;
-                        };
-                        auto issue_s = [&](int s, int jj) {  // S = Q_s K_jj^T into the shared accumulator
-                            uint32_t* tr = trace_ptr(jj, s, 768);
-                            const int itk = base + 2 * jj;
-                            if constexpr (kDebug) {
-                                if (tr) tr[0] = clk32();
-                            }
-                            mbar_wait(kv_full(slot_of(itk)), parity_of(itk), 200);
-                            if (jj == 0) mbar_wait(q_full(s), (uint32_t)(it & 1), 210 + s);
-                            if (u > 0) mbar_wait(s_free, (u - 1u) & 1u, 270 + s);
+            }
+            if constexpr (kSharedS) {
+                // ------------- generation 6 / 7: one shared S accumulator -------------
+                // Issue order per work tile (n = n_blocks):
+                //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
+                // Every S waits for `s_free` (the other warpgroup has read the previous S out of
+                // TMEM), every PV_s(j) for P_s(j).  S_s(j+1) is therefore produced while
+                // softmax_s(j) is still running.
+                int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
+                uint32_t u = 0;   // S accumulators issued so far (all tiles): s_free parity
+                uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of s/p/pv barriers
+                int it = 0;
+                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
+                    auto trace_ptr = [&](int j, int s, int off) -> uint32_t* {
+                        if constexpr (kDebug) {
+                            if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
+                                j < 32 && lane == 0)
+                                return reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + off +
+                                       (j * 2 + s) * 4;
+                        }
+                        return nullptr;
+                    };
+                    auto issue_s = [&](int s, int jj) {  // S = Q_s K_jj^T into the shared accumulator
+                        uint32_t* tr = trace_ptr(jj, s, 768);
+                        const int itk = base + 2 * jj;
+                        if constexpr (kDebug) {
+                            if (tr) tr[0] = clk32();
+                        }
+                        wait(kv_full(slot_of(itk)), parity_of(itk), 200);
+                        if (jj == 0) wait(q_full(s), (uint32_t)(it & 1), 210 + s);
+                        if (u > 0) wait(s_free, (u - 1u) & 1u, 270 + s);
+                        if constexpr (kDebug) {
+                            if (tr) tr[1] = clk32();
+                        }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            issue_qk(s, slot_of(itk));
+                            commit(s_full(s));
+                            if (jj + 1 == n_blocks) commit(q_empty(s));  // last use of Q_s
+                            if (s == 1) commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
+                        }
+                        __syncwarp();
+                        if constexpr (kDebug) {
+                            if (tr) tr[2] = clk32();
+                        }
+                        ++u;
+                    };
+                    auto issue_o = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
+                        uint32_t* tr = trace_ptr(j, s, 512);
+                        const int itv = base + 2 * j + 1;
+                        const uint32_t par = (g0 + (uint32_t)j) & 1u;
+                        wait(kv_full(slot_of(itv)), parity_of(itv), 220);
+                        wait(p_full(s), par, 230 + s);  // P_s(j) stored, O_s rescaled
+                        if constexpr (kDebug) {
+                            if (tr) tr[0] = clk32();
+                        }
+                        if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
+                            wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
+                        tc_fence_after();
+                        if constexpr (kSplitP) {
+                            if (elect_one()) issue_pv(s, slot_of(itv), j > 0, 0, 6);
+                            __syncwarp();
                             if constexpr (kDebug) {
                                 if (tr) tr[1] = clk32();
                             }
-                            tc_fence_after();
-                            if (elect_one()) {
-                                issue_qk(s, slot_of(itk));
-                                umma_commit(s_full(s));
-                                if (jj + 1 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
-                                if (s == 1) umma_commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
-                            }
-                            __syncwarp();
+                            wait(p_last(s), par, 250 + s);  // last 32 columns of P_s(j)
                             if constexpr (kDebug) {
                                 if (tr) tr[2] = clk32();
                             }
-                            ++u;
-                        };
-                        auto issue_o = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
-                            uint32_t* tr = trace_ptr(j, s, 512);
-                            const int itv = base + 2 * j + 1;
-                            const uint32_t par = (g0 + (uint32_t)j) & 1u;
-                            mbar_wait(kv_full(slot_of(itv)), parity_of(itv), 220);
-                            mbar_wait(p_full(s), par, 230 + s);  // P_s(j) stored, O_s rescaled
-                            if constexpr (kDebug) {
-                                if (tr) tr[0] = clk32();
-                            }
-                            if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
-                                mbar_wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
                             tc_fence_after();
-                            if constexpr (kSplitP) {
-                                if (elect_one()) issue_pv(s, slot_of(itv), j > 0, 0, 6);
-                                __syncwarp();
-                                if constexpr (kDebug) {
-                                    if (tr) tr[1] = clk32();
-                                }
-                                mbar_wait(p_last(s), par, 250 + s);  // last 32 columns of P_s(j)
-                                if constexpr (kDebug) {
-                                    if (tr) tr[2] = clk32();
-                                }
-                                tc_fence_after();
-                                if (elect_one()) {
-                                    issue_pv(s, slot_of(itv), true, 6, 8);
-                                    umma_commit(pv_done(s));
-                                    if (s == 1) umma_commit(kv_empty(slot_of(itv)));
-                                }
-                                __syncwarp();
-                            } else {
-                                if (elect_one()) {
-                                    issue_pv(s, slot_of(itv), j > 0, 0, 8);
-                                    umma_commit(pv_done(s));
-                                    if (s == 1) umma_commit(kv_empty(slot_of(itv)));
-                                }
-                                __syncwarp();
+                            if (elect_one()) {
+                                issue_pv(s, slot_of(itv), true, 6, 8);
+                                commit(pv_done(s));
+                                if (s == 1) commit(kv_empty(slot_of(itv)));
                             }
-                            if constexpr (kDebug) {
-                                if (tr) tr[3] = clk32();
+                            __syncwarp();
+                        } else {
+                            if (elect_one()) {
+                                issue_pv(s, slot_of(itv), j > 0, 0, 8);
+                                commit(pv_done(s));
+                                if (s == 1) commit(kv_empty(slot_of(itv)));
                             }
-                        };
-                        issue_s(0, 0);
-                        issue_s(1, 0);
-                        if (level >= 4) {
-                            if (n_blocks > 1) issue_s(0, 1);
-                            for (int j = 0; j < n_blocks; ++j) {
-                                issue_o(0, j);
-                                if (j + 1 < n_blocks) issue_s(1, j + 1);
-                                issue_o(1, j);
-                                if (j + 2 < n_blocks) issue_s(0, j + 2);
-                            }
+                            __syncwarp();
                         }
-                        base += 2 * n_blocks;
-                        g0 += (uint32_t)n_blocks;
+                        if constexpr (kDebug) {
+                            if (tr) tr[3] = clk32();
+                        }
+                    };
+                    issue_s(0, 0);
+                    issue_s(1, 0);
+                    if (level >= 4) {
+                        if (n_blocks > 1) issue_s(0, 1);
+                        for (int j = 0; j < n_blocks; ++j) {
+                            issue_o(0, j);
+                            if (j + 1 < n_blocks) issue_s(1, j + 1);
+                            issue_o(1, j);
+                            if (j + 2 < n_blocks) issue_s(0, j + 2);
+                        }
                     }
-                } else {
+                    base += 2 * n_blocks;
+                    g0 += (uint32_t)n_blocks;
+                }
+            } else {
+                // ------------------------------ generation 4b ------------------------------
                 int item = 0;    // K/V ring item counter, same order as the producer
                 uint32_t g = 0;  // KV blocks processed so far (all tiles): parity of s/p barriers
                 int it = 0;
-                for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
+                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
                     // prologue: S_s(0) = Q_s K_0^T.  S_s is free: the PV that consumed the previous
                     // tile's last P_s was issued before (in-order tensor pipe).
-                    mbar_wait(kv_full(slot_of(item)), parity_of(item), 200);
+                    wait(kv_full(slot_of(item)), parity_of(item), 200);
                     for (int s = 0; s < kQStages; ++s) {
-                        mbar_wait(q_full(s), (uint32_t)(it & 1), 210 + s);
+                        wait(q_full(s), (uint32_t)(it & 1), 210 + s);
                         tc_fence_after();
                         if (elect_one()) {
                             issue_qk(s, slot_of(item));
-                            umma_commit(s_full(s));
-                            if (n_blocks == 1) umma_commit(q_empty(s));
+                            commit(s_full(s));
+                            if (n_blocks == 1) commit(q_empty(s));
                         }
                         __syncwarp();
                     }
-                    if (elect_one()) umma_commit(kv_empty(slot_of(item)));
+                    if (elect_one()) commit(kv_empty(slot_of(item)));
                     __syncwarp();
                     ++item;
                     for (int j = 0; level >= 4 && j < n_blocks; ++j, ++g) {
                         const int it_v = item;      // V_j
                         const int it_k = item + 1;  // K_{j+1}
                         const bool has_next = (j + 1 < n_blocks);
-                        mbar_wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
+                        wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
                         for (int s = 0; s < kQStages; ++s) {
                             uint32_t* tr = nullptr;
                             if constexpr (kDebug) {
@@ -472,69 +531,52 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                                     tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 512 +
                                          (j * 2 + s) * 4;
                             }
-                            mbar_wait(p_full(s), g & 1u, 230 + s);  // P_s(j) stored, O_s rescaled
+                            wait(p_full(s), g & 1u, 230 + s);  // P_s(j) stored, O_s rescaled
                             if constexpr (kDebug) {
                                 if (tr) tr[0] = clk32();
                             }
                             if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
-                                mbar_wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
+                                wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
                             tc_fence_after();
-                            if constexpr (kSplitP) {
-                                if (elect_one()) issue_pv(s, slot_of(it_v), j > 0, 0, 6);
-                                __syncwarp();
-                                if constexpr (kDebug) {
-                                    if (tr) tr[1] = clk32();
-                                }
-                                mbar_wait(p_last(s), g & 1u, 250 + s);  // last 32 columns of P_s(j)
-                                if constexpr (kDebug) {
-                                    if (tr) tr[2] = clk32();
-                                }
-                                tc_fence_after();
-                                if (has_next && s == 0) {
-                                    mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
-                                    tc_fence_after();
-                                }
-                                if (elect_one()) {
-                                    issue_pv(s, slot_of(it_v), true, 6, 8);
-                                    if (has_next) {
-                                        issue_qk(s, slot_of(it_k));
-                                        umma_commit(s_full(s));
-                                        if (j + 2 == n_blocks) umma_commit(q_empty(s));  // last use of Q_s
-                                    } else {
-                                        umma_commit(o_full(s));
-                                    }
-                                }
-                                __syncwarp();
-                            } else {
-                                if (has_next && s == 0) {
-                                    mbar_wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
-                                    tc_fence_after();
-                                }
-                                if (elect_one()) {
-                                    issue_pv(s, slot_of(it_v), j > 0, 0, 8);
-                                    if (has_next) {
-                                        issue_qk(s, slot_of(it_k));
-                                        umma_commit(s_full(s));
-                                        if (j + 2 == n_blocks) umma_commit(q_empty(s));
-                                    } else {
-                                        umma_commit(o_full(s));
-                                    }
-                                }
-                                __syncwarp();
+                            if (elect_one()) issue_pv(s, slot_of(it_v), j > 0, 0, kSplitP ? 6 : 8);
+                            __syncwarp();
+                            if constexpr (kDebug) {
+                                if (tr) tr[1] = clk32();
                             }
+                            if constexpr (kSplitP) {
+                                wait(p_last(s), g & 1u, 250 + s);  // last 32 columns of P_s(j)
+                                tc_fence_after();
+                            }
+                            if constexpr (kDebug) {
+                                if (tr) tr[2] = clk32();
+                            }
+                            if (has_next && s == 0) {
+                                wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
+                                tc_fence_after();
+                            }
+                            if (elect_one()) {
+                                if constexpr (kSplitP) issue_pv(s, slot_of(it_v), true, 6, 8);
+                                if (has_next) {
+                                    issue_qk(s, slot_of(it_k));
+                                    commit(s_full(s));
+                                    if (j + 2 == n_blocks) commit(q_empty(s));  // last use of Q_s
+                                } else {
+                                    commit(o_full(s));
+                                }
+                            }
+                            __syncwarp();
                             if constexpr (kDebug) {
                                 if (tr) tr[3] = clk32();
                             }
                         }
                         if (elect_one()) {
-                            umma_commit(kv_empty(slot_of(it_v)));
-                            if (has_next) umma_commit(kv_empty(slot_of(it_k)));
+                            commit(kv_empty(slot_of(it_v)));
+                            if (has_next) commit(kv_empty(slot_of(it_k)));
                         }
                         __syncwarp();
                         item += has_next ? 2 : 1;
                     }
                 }
-                }  // generation 4b
             }
         }
         __syncwarp();
@@ -544,26 +586,21 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const int s = wg;                    // Q tile handled by this warpgroup
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_sel + tmem_col_s(s);
-        const uint32_t t_p = tmem_base + lane_sel + tmem_col_p(s);
+        const uint32_t t_s = tmem_base + lane_sel + tmem_col_s<kSharedS>(s);
+        const uint32_t t_p = tmem_base + lane_sel + tmem_col_p<kSharedS>(s);
         const uint32_t t_o = tmem_base + lane_sel + tmem_col_o(s);
         const float c = prm.scale_log2;
         const int kv_tail = prm.seq_len & (kBlockN - 1);  // valid keys in the last block (0 = all)
         uint32_t g = 0;  // KV blocks processed so far (all tiles)
         int it = 0;
-        // exp2-phase token (softmax_probe: one warpgroup alone needs ~1400 cycles per block, two
-        // contending ones ~2100 each): warpgroup s waits on named barrier 3+s before its exp2
-        // phase and releases barrier 3+(1-s) after it.  Warpgroup 1 pre-arrives so 0 goes first.
-        if (kPingPong && level >= 4 && s == 1) named_bar_arrive(3, 256);
 
-        for (int tile = blockIdx.x; level >= 3 && tile < tile_end; tile += gridDim.x, ++it) {
+        for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
             float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
             float l_run = 0.f;        // running row sum of exp2
             const int n_iter = (level >= 4) ? n_blocks : 1;
             for (int j = 0; j < n_iter; ++j, ++g) {
-                mbar_wait(s_full(s), g & 1u, 300 + s);
+                wait(s_full(s), g & 1u, 300 + s);
                 tc_fence_after();
-                if (FA_PINGPONG == 2 && level >= 4) named_bar_sync(3 + s, 256);  // whole step exclusive
                 uint32_t* tr = nullptr;
                 if constexpr (kDebug) {
                     if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
@@ -579,7 +616,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     // S is in registers: hand the shared accumulator to the other Q tile's next S
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_free);
+                    if (lane == 0) arrive_leader(s_free);
                 }
                 if constexpr (kDebug) {
                     if (tr) tr[1] = clk32();
@@ -618,9 +655,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                             m_run = mx;
                         }
                         // O_s must be quiescent.  Generation 4b: S_s(j) was committed after
-                        // PV_s(j-1); generation 6: wait for PV_s(j-1) explicitly.
+                        // PV_s(j-1); generation 6/7: wait for PV_s(j-1) explicitly.
                         if constexpr (kSharedS) {
-                            mbar_wait(pv_done(s), (g - 1u) & 1u, 320 + s);
+                            wait(pv_done(s), (g - 1u) & 1u, 320 + s);
                             tc_fence_after();
                         }
 #pragma unroll
@@ -642,7 +679,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const float2 c2 = make_float2(c, c);
                 const float2 nm2 = make_float2(neg_mc, neg_mc);
                 float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-                if (kPingPong && FA_PINGPONG == 1 && level >= 4) named_bar_sync(3 + s, 256);  // my turn on the MUFU
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
@@ -651,13 +687,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     else
                         exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     if constexpr (kSharedS) {
-                        // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued ~1.5 softmax
-                        // fragments ago, so this rarely spins)
+                        // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued about one
+                        // softmax fragment ago, so this rarely spins)
                         if (q == 0 && j > 0) {
                             if constexpr (kDebug) {
                                 if (tr) tr[5] = clk32();
                             }
-                            mbar_wait(pv_done(s), (g - 1u) & 1u, 330 + s);
+                            wait(pv_done(s), (g - 1u) & 1u, 330 + s);
                             tc_fence_after();
                             if constexpr (kDebug) {
                                 if (tr) tr[6] = clk32();
@@ -669,7 +705,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         tmem_wait_st();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(p_full(s));
+                        if (lane == 0) arrive_leader(p_full(s));
                         if constexpr (kDebug) {
                             if (tr) tr[3] = clk32();
                         }
@@ -678,8 +714,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(kSplitP ? p_last(s) : p_full(s));
-                if (kPingPong && level >= 4) named_bar_arrive(3 + (s ^ 1), 256);  // pass the token
+                if (lane == 0) arrive_leader(kSplitP ? p_last(s) : p_full(s));
                 if constexpr (kDebug) {
                     if (tr) tr[4] = clk32();
                 }
@@ -688,8 +723,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
             // ------------------------------- epilogue ------------------------------------
             if (level >= 4) {
-                if constexpr (kSharedS) mbar_wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
-                else mbar_wait(o_full(s), (uint32_t)(it & 1), 310 + s);
+                if constexpr (kSharedS) wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
+                else wait(o_full(s), (uint32_t)(it & 1), 310 + s);
                 tc_fence_after();
                 const float inv_l = 1.0f / l_run;
                 if constexpr (kDebug) {
@@ -706,7 +741,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(o_free(s));
+                if (lane == 0) arrive_leader(o_free(s));
                 // Two passes of 64 columns (= one TMA box) through this warpgroup's 16 KiB staging
                 // buffer, written with the TMA 128B swizzle: 16-byte chunk c of row r lives at
                 // chunk (c ^ (r & 7)) of that row.
@@ -747,16 +782,34 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
     }
 
-    // consume the last token hand-over so no named barrier is left half-arrived
-    if (kPingPong && level >= 4 && wg == 0 && (int)blockIdx.x < tile_end) named_bar_sync(3, 256);
-
     // ------------------------------------ teardown ---------------------------------------
+    // Pair: nobody may leave while the other CTA can still arrive on its barriers or while the
+    // leader's MMAs still write its tensor memory (all of them have retired once both epilogues ran).
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync();
+    else __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (kPair) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
+}
+
+template <bool kBF16, bool kDebug, bool kRagged>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+              const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+              const FwdParams prm, const FwdDebug dbg) {
+    fa_fwd_body<kBF16, kDebug, kRagged, false>(tm_q, tm_k, tm_v, tm_o, prm, dbg);
+}
+
+// Generation 7: clusters of two CTAs (tcgen05 cta_group::2).  `tm_k` must have a 64-row box.
+template <bool kBF16, bool kDebug, bool kRagged>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+fa_fwd_kernel_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                   const FwdParams prm, const FwdDebug dbg) {
+    fa_fwd_body<kBF16, kDebug, kRagged, true>(tm_q, tm_k, tm_v, tm_o, prm, dbg);
 }
 
 }  // namespace fa

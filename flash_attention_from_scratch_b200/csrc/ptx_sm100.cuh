@@ -45,15 +45,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+// kCluster: acquire at cluster scope (the barrier is also arrived on from the peer CTA of a pair)
+template <bool kCluster = false>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if constexpr (kCluster) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
     return ok != 0;
 }
 // Blocks until the phase with the given parity has completed.  With FA_HANG_GUARD the spin is
@@ -74,10 +86,11 @@ __device__ __forceinline__ void diag_record(uint32_t a, uint32_t b, uint32_t c, 
     __threadfence_system();
 }
 #endif
+template <bool kCluster = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
 #if FA_HANG_GUARD
     for (uint32_t it = 0; it < (1u << 22); ++it) {
-        if (mbar_try_wait(bar, parity)) return;
+        if (mbar_try_wait<kCluster>(bar, parity)) return;
     }
     diag_record(0xDEAD0000u | (uint32_t)tag, parity, threadIdx.x, blockIdx.x);
     printf("[fa] mbarrier timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
@@ -85,7 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     __trap();
 #else
     (void)tag;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait<kCluster>(bar, parity)) {
     }
 #endif
 }
@@ -224,6 +237,86 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      bar)
                  : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// CTA pairs (thread-block cluster of 2, tcgen05 .cta_group::2): one thread of the even CTA issues
+// an MMA with M = 256 whose accumulator rows [0,128) live in its own tensor memory and rows
+// [128,256) in the odd CTA's; A comes from each CTA's own shared / tensor memory, B is split in
+// halves along N between the two CTAs' shared memories (same offsets in both).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    cluster_arrive();
+    cluster_wait();
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once all
+// tcgen05 ops issued so far by this thread (for the CTA pair) have retired.
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(bar), "h"(cta_mask)
+        : "memory");
+}
+// TMA load whose completion bytes are credited to the mbarrier at cluster address `bar_cluster`
+// (normally the even CTA's barrier, so that the MMA issuer sees both CTAs' halves arrive).
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst_smem, const CUtensorMap* map,
+                                                 uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst_smem), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
 // TMEM -> registers: each lane of the warp reads 32 consecutive 32-bit columns of "its" TMEM lane

@@ -82,6 +82,19 @@ int fa_kernel_info(int* smem_bytes, int* threads, int* rows_per_cta, int* tmem_c
 /* Number of kernel launches issued through this library since load (all threads). */
 int64_t fa_launch_count(void);
 
+/* Which kernel a launch uses.  The reference selects one of its 85 template instantiations with the
+ * kernel_cfg map lookup (flash_attention.cu:59-62); this library has two machine mappings of the same
+ * arithmetic and picks by shape:
+ *   FA_MODE_AUTO   (default): CTA pairs when seq_len > 256, single CTAs otherwise
+ *   FA_MODE_SINGLE one CTA per SM, work tile = 256 query rows
+ *   FA_MODE_PAIR   clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
+ * Process-wide; returns the previous mode (or -1 for an invalid argument).  The environment variable
+ * FA_SM100_MODE=auto|single|pair sets the initial value. */
+#define FA_MODE_AUTO 0
+#define FA_MODE_SINGLE 1
+#define FA_MODE_PAIR 2
+int fa_set_kernel_mode(int mode);
+
 /* Bring-up entry: runs the debug instantiation with explicit descriptor knobs and a dump buffer
  * (see FwdDebug in csrc/fa_fwd_sm100.cuh).  knobs[7] = bring-up level (1 setup only, 2 TMA,
  * 3 QK^T, >= 4 everything; knobs[0..6] are ignored); `dump` and `diag` should be host-mapped

@@ -36,7 +36,8 @@ def test_library_is_sm100a_with_tcgen05_and_tma(lib):
     assert "EF_CUDA_SM100" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
         assert mnemonic in sass, mnemonic
-    assert "HMMA." not in sass  # no legacy mma.sync path
+    assert "UTCHMMA.2CTA" in sass  # the CTA-pair kernel (tcgen05 cta_group::2)
+    assert re.search(r"(?<![A-Z])HMMA\.", sass) is None  # no legacy mma.sync path
 
 
 def test_kernel_info(lib):

@@ -70,6 +70,26 @@ def test_matches_sdpa(dtype, B, N, H):
 
 
 # ------------------------------------------------------------------ the reference's own test, verbatim shape
+@pytest.mark.parametrize("mode", ["single", "pair"])
+@pytest.mark.parametrize("dtype,B,N,H", [(torch.bfloat16, 1, 128, 2), (torch.float16, 2, 200, 3),
+                                         (torch.bfloat16, 2, 512, 5), (torch.float16, 1, 640, 4),
+                                         (torch.bfloat16, 3, 1000, 7), (torch.bfloat16, 2, 2048, 40)])
+def test_both_machine_mappings(mode, dtype, B, N, H):
+    """AUTO picks CTA pairs (cta_group::2) for seq_len > 256 and single CTAs below; both mappings must
+    give the same answer at every shape, including pairs whose second CTA has no valid query rows."""
+    from flash_attention_from_scratch_b200 import _lib
+    q, k, v = rand_qkv((B, N, H, 128), dtype, seed=N + H)
+    prev = _lib.set_kernel_mode(_lib.MODE_SINGLE if mode == "single" else _lib.MODE_PAIR)
+    try:
+        out = flash_attention.forward(cfg_for(dtype), q, k, v)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_kernel_mode(prev)
+    ref = sdpa32(q, k, v)
+    atol = 1e-3 if N >= 512 else 2e-3
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=atol)
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_reference_suite_shape_and_criterion(dtype):
     # py/flash_helpers/test/test.py:19-61: (16, 2048, 16, 128), every config of get_kernels_to_build()

@@ -11,15 +11,14 @@ sys.path.insert(0, str(ROOT))
 from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 
 VARIANTS = {
-    # name: defines
-    "g4b": {"FA_SHARED_S": 0},
-    "g6": {},
-    "g6_emu4_4": {"FA_EMU_PAIRS_LAST": 4},
-    "g6_emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
-    "g6_emu2": {"FA_EMU_PAIRS": 2},
-    "g6_emu0": {"FA_EMU_PAIRS": 0},
-    "g6_nosplit": {"FA_SPLIT_P": 0},
-    "g6_r200": {"FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 104},
+    # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
+    "base": {},
+    "g4b": {"FA_SHARED_S": 0},   # single-CTA kernel = generation 4b instead of 6
+    "emu4_4": {"FA_EMU_PAIRS_LAST": 4},
+    "emu2": {"FA_EMU_PAIRS": 2},
+    "emu0": {"FA_EMU_PAIRS": 0},
+    "emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
+    "nosplit": {"FA_SPLIT_P": 0},
 }
 
 

@@ -31,10 +31,11 @@ def swizzled_image(t):
     c ^ (r & 7) of that row inside its 16 KiB half."""
     import torch
     halves = []
+    rows = t.shape[0]
     for h in range(2):
-        x = t[:, 64 * h: 64 * h + 64].contiguous().view(128, 8, 8)  # rows, chunks, 8 elems
+        x = t[:, 64 * h: 64 * h + 64].contiguous().view(rows, 8, 8)  # rows, chunks, 8 elems
         out = torch.empty_like(x)
-        for r in range(128):
+        for r in range(rows):
             for c in range(8):
                 out[r, c ^ (r & 7)] = x[r, c]
         halves.append(out.reshape(-1))
@@ -66,7 +67,10 @@ def run_one(args):
     kf = k[0, :, 0].float().cpu()
     vf = v[0, :, 0].float().cpu()
     q_img = swizzled_image(q[0, :128, 0].cpu())
-    k_img = swizzled_image(k[0, :128, 0].cpu())
+    # CTA pairs (seq_len > 256 unless FA_SM100_MODE says otherwise): CTA 0 holds keys 0..63 of K_0
+    mode = os.environ.get("FA_SM100_MODE", "auto")
+    pair = mode == "pair" or (mode != "single" and N > 256)
+    k_img = swizzled_image(k[0, :(64 if pair else 128), 0].cpu())
     ref = None
     if level >= 4:
         ref = torch.nn.functional.scaled_dot_product_attention(
@@ -86,7 +90,8 @@ def run_one(args):
     if level == 2:
         words = dump.view(torch.int32)
         res["q_smem_match"] = bool((words[:8192] == q_img).all().item())
-        res["k_smem_match"] = bool((words[8192:16384] == k_img).all().item())
+        res["k_smem_match"] = bool((words[8192:8192 + k_img.numel()] == k_img).all().item())
+        res["pair"] = pair
         res["q_smem_nonzero"] = int((words[:8192] != 0).sum().item())
     if level >= 3:
         S0 = qf @ kf[:128].T                       # rows 0..255 of work tile 0, first KV block

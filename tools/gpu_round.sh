@@ -18,6 +18,8 @@ PY
 if [ $? -ne 0 ]; then echo "GATE FAILED"; exit 1; fi
 FA_SM100_LIB=$GUARD timeout 300 python tools/quick_bench.py --shapes "2,512,4;1,128,2;3,1280,5;4,4096,32" --reps 3 --warmup 1 --check 2>&1 | tail -6
 if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "GUARDED PRODUCTION RUN FAILED"; exit 1; fi
-timeout 900 python tools/sweep_variants.py --shapes "${SWEEP_SHAPES:-4,4096,32;16,1024,16}" --reps 20 --out gpurun_out/sweep_${TAG:-g6}.json 2>&1 | tail -30
+FA_SM100_MODE=pair FA_SM100_LIB=$GUARD timeout 300 python tools/quick_bench.py --shapes "1,128,2;2,200,3" --reps 2 --warmup 1 --check 2>&1 | tail -3
+if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "GUARDED PRODUCTION RUN FAILED"; exit 1; fi
+timeout 900 python tools/sweep_variants.py --shapes "${SWEEP_SHAPES:-4,4096,32;16,1024,16}" --modes "${SWEEP_MODES:-single,pair}" --reps 20 --out gpurun_out/sweep_${TAG:-g6}.json 2>&1 | tail -40
 timeout 200 python tools/gpu_trace.py > gpurun_out/trace_${TAG:-g6}.txt 2>&1; tail -3 gpurun_out/trace_${TAG:-g6}.txt | cut -c1-900
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu_${TAG:-g6}.txt 2>&1; tail -4 gpurun_out/pytest_gpu_${TAG:-g6}.txt

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "sweep.json"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--modes", default="auto", help="comma list of FA_SM100_MODE values (auto, single, pair)")
     args = ap.parse_args()
     vdir = ROOT / "flash_attention_from_scratch_b200" / "csrc" / "variants"
     rows = []
@@ -23,21 +24,23 @@ def main():
         name = lib.stem[len("libfa_"):]
         if args.only and name not in args.only.split(","):
             continue
-        env = dict(os.environ, FA_SM100_LIB=str(lib))
-        p = subprocess.run([sys.executable, str(ROOT / "tools" / "quick_bench.py"), "--shapes", args.shapes,
-                            "--reps", str(args.reps), "--check"], capture_output=True, text=True, env=env,
-                           timeout=300)
-        for line in p.stdout.splitlines():
-            try:
-                r = json.loads(line)
-            except Exception:  # noqa: BLE001
-                continue
-            r["variant"] = name
-            rows.append(r)
-            print(f"{name:16s} {r['shape']} mean {r['tflops_mean']:.1f} best {r['tflops_best']:.1f} TF/s  "
-                  f"maxdiff16 {r.get('maxdiff_vs_sdpa16')}", flush=True)
-        if p.returncode != 0:
-            print(name, "FAILED", p.stderr[-500:], flush=True)
+        for mode in args.modes.split(","):
+            env = dict(os.environ, FA_SM100_LIB=str(lib), FA_SM100_MODE=mode)
+            p = subprocess.run([sys.executable, str(ROOT / "tools" / "quick_bench.py"), "--shapes", args.shapes,
+                                "--reps", str(args.reps), "--check"], capture_output=True, text=True, env=env,
+                               timeout=300)
+            for line in p.stdout.splitlines():
+                try:
+                    r = json.loads(line)
+                except Exception:  # noqa: BLE001
+                    continue
+                r["variant"] = name
+                r["mode"] = mode
+                rows.append(r)
+                print(f"{name:14s} {mode:6s} {r['shape']} mean {r['tflops_mean']:.1f} best {r['tflops_best']:.1f} "
+                      f"TF/s  maxdiff16 {r.get('maxdiff_vs_sdpa16')}", flush=True)
+            if p.returncode != 0:
+                print(name, mode, "FAILED", p.stderr[-500:], flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(rows, f, indent=1)
