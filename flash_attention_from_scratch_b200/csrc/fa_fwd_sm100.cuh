@@ -196,7 +196,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kMaxStages + s); };  // generation 6/7
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
 
-    auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait<kPair>(bar, parity, tag); };
+    auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait(bar, parity, tag); };
     auto arrive_leader = [&](uint32_t bar) {  // one arrival on the leader CTA's copy of `bar`
         if constexpr (kPair) mbar_arrive_cluster(mapa_shared(bar, 0));
         else mbar_arrive(bar);

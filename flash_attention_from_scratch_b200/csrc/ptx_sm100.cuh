@@ -45,27 +45,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-// kCluster: acquire at cluster scope (the barrier is also arrived on from the peer CTA of a pair)
-template <bool kCluster = false>
+// The default (.acquire.cta) form is also what the CTA-pair kernel uses: an acquire at cluster scope
+// makes ptxas emit CCTL.IVALL (L1 invalidate) after EVERY wait and MEMBAR.ALL.GPU before every remote
+// arrive -- measured 2x slower end to end -- and it is not needed: everything that crosses the two CTAs
+// travels through the async / tensor proxies (TMA complete_tx, tcgen05.commit, tensor memory) and is
+// ordered by the tcgen05 fences, never through generic-proxy memory.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    if constexpr (kCluster) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
     return ok != 0;
 }
 // Blocks until the phase with the given parity has completed.  With FA_HANG_GUARD the spin is
@@ -86,11 +79,10 @@ __device__ __forceinline__ void diag_record(uint32_t a, uint32_t b, uint32_t c, 
     __threadfence_system();
 }
 #endif
-template <bool kCluster = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
 #if FA_HANG_GUARD
     for (uint32_t it = 0; it < (1u << 22); ++it) {
-        if (mbar_try_wait<kCluster>(bar, parity)) return;
+        if (mbar_try_wait(bar, parity)) return;
     }
     diag_record(0xDEAD0000u | (uint32_t)tag, parity, threadIdx.x, blockIdx.x);
     printf("[fa] mbarrier timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
@@ -98,7 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     __trap();
 #else
     (void)tag;
-    while (!mbar_try_wait<kCluster>(bar, parity)) {
+    while (!mbar_try_wait(bar, parity)) {
     }
 #endif
 }
@@ -267,8 +259,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-                 : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),

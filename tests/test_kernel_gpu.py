@@ -81,7 +81,9 @@ def test_both_machine_mappings(mode, dtype, B, N, H):
     q, k, v = rand_qkv((B, N, H, 128), dtype, seed=N + H)
     prev = _lib.set_kernel_mode(_lib.MODE_SINGLE if mode == "single" else _lib.MODE_PAIR)
     try:
-        out = flash_attention.forward(cfg_for(dtype), q, k, v)
+        # ragged lengths are an extension of the C ABI: the operator keeps the reference's
+        # `% B_r` error for reference-style configs, so pass no config for those
+        out = flash_attention.forward(cfg_for(dtype) if N % 128 == 0 else None, q, k, v)
         torch.cuda.synchronize()
     finally:
         _lib.set_kernel_mode(prev)
