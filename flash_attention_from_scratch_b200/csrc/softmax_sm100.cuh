@@ -34,6 +34,26 @@ __device__ __forceinline__ float row_max_128(const uint32_t (&sr)[4][32]) {
                  fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
 }
 
+// Row max of fragments [kFirst, kFirst + kCount) of a row (two chains per fragment).
+template <int kFirst, int kCount>
+__device__ __forceinline__ float row_max_frags(const uint32_t (&sr)[4][32]) {
+    float mxs[2 * kCount];
+#pragma unroll
+    for (int u = 0; u < 2 * kCount; ++u) mxs[u] = __uint_as_float(sr[kFirst + (u >> 1)][(u & 1) * 16]);
+#pragma unroll
+    for (int q = 0; q < kCount; ++q) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            mxs[2 * q] = fmaxf(mxs[2 * q], __uint_as_float(sr[kFirst + q][i]));
+            mxs[2 * q + 1] = fmaxf(mxs[2 * q + 1], __uint_as_float(sr[kFirst + q][16 + i]));
+        }
+    }
+    float m = mxs[0];
+#pragma unroll
+    for (int u = 1; u < 2 * kCount; ++u) m = fmaxf(m, mxs[u]);
+    return m;
+}
+
 // One 32-column fragment: x = S*c - m*c (FFMA2), p = 2^x (MUFU or FMA-pipe polynomial for `kEmu`
 // of the 16 pairs), two fp32 partial row sums (FADD2), 16 packed 16-bit pairs for tcgen05.st.
 //   kVariant 0: one fused loop per pair (the compiler interleaves freely)

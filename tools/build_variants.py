@@ -13,7 +13,8 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 VARIANTS = {
     # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
     "base": {},
-    "g4b": {"FA_SHARED_S": 0},   # single-CTA kernel = generation 4b instead of 6
+    "prefetch": {"FA_PREFETCH_S": 1},     # generation 8 softmax loop (rejected)
+    "g4b": {"FA_SHARED_S": 0},            # single-CTA kernel = generation 4b instead of 6
     "emu4_4": {"FA_EMU_PAIRS_LAST": 4},
     "emu2": {"FA_EMU_PAIRS": 2},
     "emu0": {"FA_EMU_PAIRS": 0},
