@@ -29,10 +29,18 @@
 //       The even CTA's MMA warp issues M = 256 MMAs for both; each CTA keeps its own Q tiles,
 //       softmax and epilogue but loads only HALF of every K block (64 keys) and V block (64 of
 //       the 128 d columns): per MMA a CTA reads 6 KiB of smem operands instead of 8, and TMA
-//       writes half as much.  Reason: tools/mma_probe.cu shows an isolated 128x128x16 SS MMA runs
-//       at the nominal 64 clk, but at 128 B/clk it needs ALL of the shared-memory bandwidth, and
-//       in the attention loop (TMA writes of K/V arriving at the same time) the cycle trace showed
-//       ~100 clk per QK^T MMA: shared-memory bandwidth, not the tensor core, paced generation 4b/6.
+//       writes half as much.
+//   generation 9  (FA_UNIFORM_WARP, FA_LD_SPLIT; both mappings): the warp index is broadcast with
+//       shfl so that ptxas keeps the MMA warp's counters and descriptors in UNIFORM registers, and
+//       the softmax warps reduce the row max of S[:, :64] while S[:, 64:] is still being fetched.
+//       Why: a tensor-pipe observer (tools/gpu_trace.py) showed every QK^T group occupying the pipe
+//       for ~930 clk instead of 512, tools/mma_probe.cu showed that no interference (register math,
+//       bulk copies, tcgen05.ld, random operands, group alternation) slows a tcgen05.mma down, and
+//       switching the softmax arithmetic / TMA / S read-out off in the debug kernel changed nothing:
+//       the time went into ~26 R2UR per group that ptxas placed between the barrier wait and the
+//       first UTCHMMA because it could not prove the issuing warp's values uniform.  With the hint
+//       the single-CTA mapping gained 13 % (1279 -> 1450 TFLOP/s), the pair 2 % (1431 -> 1459)
+//       (profiles/r01_g9_notes.md).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -103,6 +111,14 @@ constexpr bool kSharedSDefault = FA_SHARED_S != 0;
                               // shared S accumulator ~1500 clk longer per block, which stalls the other
                               // Q tile's S issue; kept for the record, off by default.
 #endif
+#ifndef FA_UNIFORM_WARP
+#define FA_UNIFORM_WARP 1
+#endif
+#ifndef FA_LD_SPLIT
+#define FA_LD_SPLIT 1         // 1: fetch S in two halves and reduce the row max of the first 64 columns
+                              // while the tcgen05.ld of the last 64 is in flight (TMEM reads run at
+                              // ~64 B/clk per sub-partition: 256 clk for the 16 KiB a warp owns)
+#endif
 static_assert(kKVStages >= 4, "generation 6/7 keep V_j, K_j+1, V_j+1, K_j+2 in flight");
 
 // Tensor-memory column map (512 columns, base 0).
@@ -132,7 +148,11 @@ struct FwdDebug {
     uint32_t level;   // 1: setup/teardown only, 2: + TMA Q_0,K_0, 3: + S = QK^T, >= 4: everything,
                       // 5: everything + cycle trace of CTA 0 / tile 0 (words from kTraceBase on:
                       // softmax [stage][block<32][8 events], PV issue [block<32][stage][4 events],
-                      // S issue [block<32][stage][4 events])
+                      // S issue [block<32][stage][4 events], tensor-pipe observer [block<32][4 events])
+                      // 6..9: level 5 with parts of the kernel switched off (timing ablations, results
+                      // are garbage): 6 = no softmax arithmetic (S is read, a constant P is stored),
+                      // 7 = K/V ring slots are not refilled by TMA after the first pass, 8 = 6 + 7,
+                      // 9 = 8 + S is not read out of tensor memory either
     uint32_t* diag;   // host-mapped diagnostics ring (hang-guard builds)
 };
 
@@ -162,6 +182,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                             const FwdParams& prm, const FwdDebug& dbg) {
     constexpr bool kSharedS = kPair || kSharedSDefault;
     constexpr bool kPrefetch = kSharedS && (FA_PREFETCH_S != 0);
+    constexpr bool kLdSplit = !kPrefetch && !kRagged && (FA_LD_SPLIT != 0);
     constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;      // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
@@ -178,7 +199,13 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
         __trap();
     }
 
+#if FA_UNIFORM_WARP
+    // broadcast from lane 0: ptxas then knows the warp index (and every role branch on it) is
+    // warp-uniform and keeps the MMA warp's counters and descriptors in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#else
     const int warp = threadIdx.x >> 5;
+#endif
     const int lane = threadIdx.x & 31;
     const int wg = warp >> 2;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;  // CTA inside its pair
@@ -317,7 +344,10 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     const int slot = item % kStages;
                     const uint32_t use = item / kStages;
                     wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
-                    if (elect_one()) {
+                    if (kDebug && level >= 7 && item >= kStages) {
+                        // ablation: keep the barrier protocol, skip the copy (the slot keeps old data)
+                        if (is_leader && elect_one()) mbar_arrive(kv_full(slot));
+                    } else if (elect_one()) {
                         const uint32_t dst = smem_base + kSmemKV + slot * kSlotBytes;
                         if (is_leader) mbar_arrive_expect_tx(kv_full(slot), kTileBytes);
                         if (kPair && !is_k) {  // V: one box, this CTA's 64 d columns of all 128 keys
@@ -360,10 +390,14 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             // (SBO); one k-step = 16 kv rows = 2 KiB.  P (A operand in TMEM): 8 columns/k-step.
             // Pair: the B descriptors cover this CTA's half (64 keys of K / 64 d columns of V);
             // the peer CTA's tensor core reads the same offsets of its own shared memory.
-            auto issue_qk = [&](int s, int slot) {
+            auto k_desc = [&](int slot) {
+                return umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, 16, 1024);
+            };
+            auto v_desc = [&](int slot) {
+                return umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, kHalfBytes, 1024);
+            };
+            auto issue_qk_b = [&](int s, uint64_t b0) {
                 const uint64_t a0 = umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, 16, 1024);
-                const uint64_t b0 =
-                    umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, 16, 1024);
 #pragma unroll
                 for (int k = 0; k < kHeadDim / 16; ++k) {
                     const uint32_t a_off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
@@ -374,9 +408,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         umma_ss(tmem_base + tmem_col_s<kSharedS>(s), a0 + a_off, b0 + b_off, idesc_qk, k > 0);
                 }
             };
-            auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
-                const uint64_t b0 = umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes,
-                                                         kHalfBytes, 1024);
+            auto issue_qk = [&](int s, int slot) { issue_qk_b(s, k_desc(slot)); };
+            auto issue_pv_b = [&](int s, uint64_t b0, bool accumulate, int k_begin, int k_end) {
 #pragma unroll
                 for (int k = k_begin; k < k_end; ++k) {
                     const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
@@ -387,6 +420,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
                                 b0 + ((k * 2048) >> 4), idesc_pv, acc);
                 }
+            };
+            auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
+                issue_pv_b(s, v_desc(slot), accumulate, k_begin, k_end);
             };
             auto slot_of = [&](int i) { return i % kStages; };
             auto parity_of = [&](int i) { return (uint32_t)((i / kStages) & 1); };
@@ -418,7 +454,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
                     auto trace_ptr = [&](int j, int s, int off) -> uint32_t* {
                         if constexpr (kDebug) {
-                            if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
+                            if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
                                 j < 32 && lane == 0)
                                 return reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + off +
                                        (j * 2 + s) * 4;
@@ -428,6 +464,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     auto issue_s = [&](int s, int jj) {  // S = Q_s K_jj^T into the shared accumulator
                         uint32_t* tr = trace_ptr(jj, s, 768);
                         const int itk = base + 2 * jj;
+                        const uint64_t kd = k_desc(slot_of(itk));
                         if constexpr (kDebug) {
                             if (tr) tr[0] = clk32();
                         }
@@ -439,7 +476,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                         tc_fence_after();
                         if (elect_one()) {
-                            issue_qk(s, slot_of(itk));
+                            issue_qk_b(s, kd);
                             commit(s_full(s));
                             if (jj + 1 == n_blocks) commit(q_empty(s));  // last use of Q_s
                             if (s == 1) commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
@@ -453,6 +490,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     auto issue_o = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
                         uint32_t* tr = trace_ptr(j, s, 512);
                         const int itv = base + 2 * j + 1;
+                        const uint64_t vd = v_desc(slot_of(itv));
                         const uint32_t par = (g0 + (uint32_t)j) & 1u;
                         wait(kv_full(slot_of(itv)), parity_of(itv), 220);
                         wait(p_full(s), par, 230 + s);  // P_s(j) stored, O_s rescaled
@@ -463,7 +501,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                             wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
                         tc_fence_after();
                         if constexpr (kSplitP) {
-                            if (elect_one()) issue_pv(s, slot_of(itv), j > 0, 0, 6);
+                            if (elect_one()) issue_pv_b(s, vd, j > 0, 0, 6);
                             __syncwarp();
                             if constexpr (kDebug) {
                                 if (tr) tr[1] = clk32();
@@ -474,14 +512,14 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                             }
                             tc_fence_after();
                             if (elect_one()) {
-                                issue_pv(s, slot_of(itv), true, 6, 8);
+                                issue_pv_b(s, vd, true, 6, 8);
                                 commit(pv_done(s));
                                 if (s == 1) commit(kv_empty(slot_of(itv)));
                             }
                             __syncwarp();
                         } else {
                             if (elect_one()) {
-                                issue_pv(s, slot_of(itv), j > 0, 0, 8);
+                                issue_pv_b(s, vd, j > 0, 0, 8);
                                 commit(pv_done(s));
                                 if (s == 1) commit(kv_empty(slot_of(itv)));
                             }
@@ -535,7 +573,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         for (int s = 0; s < kQStages; ++s) {
                             uint32_t* tr = nullptr;
                             if constexpr (kDebug) {
-                                if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
+                                if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
                                     j < 32 && lane == 0)
                                     tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 512 +
                                          (j * 2 + s) * 4;
@@ -584,6 +622,32 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                         __syncwarp();
                         item += has_next ? 2 : 1;
+                    }
+                }
+            }
+        } else if (warp == 10) {
+            // ====================== tensor-pipe observer (cycle trace only) ======================
+            // Level 5: an otherwise idle warp watches the completion barriers of the first work tile
+            // in the order the in-order tensor pipe retires the groups,
+            //     S_0(j)  PV_0(j-1)  S_1(j)  PV_1(j-1)        (j >= 1),
+            // so the deltas between consecutive stamps are the pipe time of each 8-MMA group while
+            // the pipe is backlogged.  Bounded polls: a missed phase gives a zero, never a hang.
+            if constexpr (kDebug && kSharedS) {
+                if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && lane == 0 && cta_lin < tile_end) {
+                    uint32_t* ob = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 1024;
+                    auto stamp = [&](uint32_t bar, uint32_t parity) -> uint32_t {
+                        for (int spin = 0; spin < (1 << 20); ++spin)
+                            if (mbar_try_wait(bar, parity)) return clk32();
+                        return 0u;
+                    };
+                    const int nb = min(n_blocks, 32);
+                    ob[0] = stamp(s_full(0), 0u);
+                    ob[2] = stamp(s_full(1), 0u);
+                    for (int j = 1; j < nb; ++j) {
+                        ob[j * 4 + 0] = stamp(s_full(0), (uint32_t)j & 1u);
+                        ob[j * 4 + 1] = stamp(pv_done(0), (uint32_t)(j - 1) & 1u);
+                        ob[j * 4 + 2] = stamp(s_full(1), (uint32_t)j & 1u);
+                        ob[j * 4 + 3] = stamp(pv_done(1), (uint32_t)(j - 1) & 1u);
                     }
                 }
             }
@@ -636,22 +700,46 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 }
                 uint32_t* tr = nullptr;
                 if constexpr (kDebug) {
-                    if (level == 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
+                    if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
                         (warp & 3) == 0 && lane == 0)
                         tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + (s * 32 + j) * 8;
                     if (tr) tr[0] = clk32();
                 }
-                if constexpr (!kPrefetch) {
+                float m_lo = -INFINITY;  // kLdSplit: row max of columns [0, 64)
+                if (kDebug && level >= 9) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sr[q][i] = 0u;
+                } else if constexpr (kLdSplit) {
+                    tmem_ld_32x32b_x32(t_s, sr[0]);
+                    tmem_ld_32x32b_x32(t_s + 32, sr[1]);
+                    tmem_wait_ld();
+                    tmem_ld_32x32b_x32(t_s + 64, sr[2]);
+                    tmem_ld_32x32b_x32(t_s + 96, sr[3]);
+                    m_lo = row_max_frags<0, 2>(sr);
+                    tmem_wait_ld();
+                } else {
+                    if constexpr (!kPrefetch) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
+                    }
+                    tmem_ld_32x32b_x32(t_s + 3 * 32, sr[3]);
+                    tmem_wait_ld();
                 }
-                tmem_ld_32x32b_x32(t_s + 3 * 32, sr[3]);
-                tmem_wait_ld();
                 if constexpr (kSharedS) {
                     // S is in registers: hand the shared accumulator to the other Q tile's next S
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) arrive_leader(s_free);
+                    if constexpr (kLdSplit) {
+                        // ptxas hoists the arrive (and with it the stall on the last tcgen05.ld)
+                        // above the reduction of the first half; a never-true dependency on m_lo
+                        // keeps it behind
+                        const uint32_t skew = (__float_as_uint(m_lo) == 0x7fc12345u) ? 8u : 0u;
+                        if (lane == 0) arrive_leader(s_free + skew);
+                    } else {
+                        if (lane == 0) arrive_leader(s_free);
+                    }
                 }
                 if constexpr (kDebug) {
                     if (tr) tr[1] = clk32();
@@ -670,8 +758,13 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                     if (level == 3) break;
                 }
+                const bool no_math = kDebug && level >= 6 && level != 7;  // timing ablation
                 float mx;
-                if constexpr (kPrefetch) {
+                if (no_math) {
+                    mx = 0.f;
+                } else if constexpr (kLdSplit) {
+                    mx = fmaxf(m_lo, row_max_frags<2, 2>(sr));
+                } else if constexpr (kPrefetch) {
                     mx = fmaxf(m012, row_max_frags<3, 1>(sr));
                 } else {
                     mx = row_max_128(sr);
@@ -716,7 +809,10 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[16];
-                    if (q == 3) {
+                    if (no_math) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0x3c003c00u;
+                    } else if (q == 3) {
                         exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                         if constexpr (kPrefetch) {
                             // fragments 0..2 now hold S_s(j+1): their row max shares this basic block

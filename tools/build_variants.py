@@ -13,6 +13,11 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 VARIANTS = {
     # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
     "base": {},
+    "nouwarp": {"FA_UNIFORM_WARP": 0},    # warp index straight from threadIdx (generation 7 code shape)
+    "emu6": {"FA_EMU_PAIRS": 6},
+    "emu8": {"FA_EMU_PAIRS": 8},
+    "emu6_4": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 4},
+    "noldsplit": {"FA_LD_SPLIT": 0},      # S fetched with one wait, row max afterwards
     "prefetch": {"FA_PREFETCH_S": 1},     # generation 8 softmax loop (rejected)
     "g4b": {"FA_SHARED_S": 0},            # single-CTA kernel = generation 4b instead of 6
     "emu4_4": {"FA_EMU_PAIRS_LAST": 4},

@@ -20,15 +20,16 @@ TRACE_BASE = 2 * 128 * 128 + 512
 
 def main():
     B, N, H = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (4, 4096, 32)))
+    level = int(os.environ.get("FA_TRACE_LEVEL", "5"))  # 6..9: ablations, see FwdDebug::level
     lib = _lib.load()
     torch.manual_seed(0)
     q = torch.randn(B, N, H, 128, device="cuda", dtype=torch.bfloat16)
     k = torch.randn_like(q)
     v = torch.randn_like(q)
     o = torch.empty_like(q)
-    dump = torch.zeros(TRACE_BASE + 1024, device="cuda", dtype=torch.float32)
+    dump = torch.zeros(TRACE_BASE + 1152, device="cuda", dtype=torch.float32)
     diag = torch.zeros(256, device="cuda", dtype=torch.int32)
-    knobs = (C.c_uint32 * 8)(0, 0, 0, 0, 0, 0, 0, 5)
+    knobs = (C.c_uint32 * 8)(0, 0, 0, 0, 0, 0, 0, level)
     sb, sn, sh, _ = q.stride()
     for _ in range(2):
         rc = lib.fa_fwd_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, N, H, 128, sb, sn,
@@ -65,13 +66,28 @@ def main():
                   f"{r['mma_plast_lat']:6d} {r['mma_tail_issue']:6d} | period {r['period']} | pvwait {r['pv_wait']} "
                   f"s_blocked {r['s_issue_blocked']} s_issue->seen {r['s_issue_to_seen']}")
     import statistics as st
+    # tensor-pipe observer: retirement stamps of S_0(j), PV_0(j-1), S_1(j), PV_1(j-1); the delta to the
+    # previous stamp is the pipe time of that 8-MMA group while the pipe is backlogged
+    ob = tr[1024:1152].reshape(32, 4)[:nb]
+    pipe_rows = []
+    print("blk | retire-to-retire: S_0(j)  PV_0(j-1)  S_1(j)  PV_1(j-1) | S_0(j) seen by softmax after retire")
+    for j in range(2, nb - 1):
+        if 0 in ob[j] or 0 in ob[j - 1]:
+            continue
+        pr = {"j": j, "dS0": d(ob[j, 0], ob[j - 1, 3]), "dPV0": d(ob[j, 1], ob[j, 0]), "dS1": d(ob[j, 2], ob[j, 1]),
+              "dPV1": d(ob[j, 3], ob[j, 2]), "s0_seen_lag": d(sm[0, j, 0], ob[j, 0])}
+        pipe_rows.append(pr)
+        print(f"{j:3d} | {pr['dS0']:6d} {pr['dPV0']:6d} {pr['dS1']:6d} {pr['dPV1']:6d} | {pr['s0_seen_lag']:6d}")
+    if pipe_rows:
+        pk = ["dS0", "dPV0", "dS1", "dPV1", "s0_seen_lag"]
+        print("PIPE_MEDIANS", json.dumps({k_: st.median(r[k_] for r in pipe_rows if r["j"] >= 4) for k_ in pk}))
     keys = ["ld", "max", "exp96", "exp32", "wait_next_S", "mma_pfull_lat", "mma_pv6_issue", "mma_plast_lat",
             "mma_tail_issue", "period", "pv_wait", "s_issue_blocked", "s_issue_to_seen"]
     summ = {k_: st.median(r[k_] for r in rows if r["j"] >= 4) for k_ in keys}
     print("MEDIANS", json.dumps(summ))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "trace.json"), "w") as f:
-        json.dump({"shape": [B, N, H, 128], "rows": rows, "medians": summ}, f)
+    with open(os.path.join(ROOT, "gpurun_out", os.environ.get("FA_TRACE_OUT", "trace.json")), "w") as f:
+        json.dump({"shape": [B, N, H, 128], "level": level, "rows": rows, "medians": summ, "pipe_rows": pipe_rows}, f)
 
 
 if __name__ == "__main__":

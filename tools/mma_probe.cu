@@ -13,6 +13,15 @@
 // descriptor conventions (in particular the .cta_group::2 operand split) are pinned before the
 // attention kernel relies on them.
 //
+// Second part (added after the tensor-pipe observer of tools/gpu_trace.py showed ~117 clk per QK^T MMA
+// inside the attention kernel while P V MMAs ran at ~64): the same loops with an interference agent in
+// warps 4..7, to find out WHAT slows the SS MMAs down in situ:
+//     noise 0 none   1 softmax-like FFMA/MUFU register math   2 bulk copies global -> shared at full rate
+//     3 bulk copies paced like the kernel's K/V stream (16 KiB per 700 clk)   4 tcgen05.ld of 128 columns
+//     5 = 1 + 3 + 4 together
+// `rnd` fills the operands with random normal-ish bf16 instead of small integers (data-dependent power).
+// Mode bit 2 (TS only): B is MN-major like the kernel's V operand.
+//
 // build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -DFA_HANG_GUARD=1
 //        -I flash_attention_from_scratch_b200/csrc -o tools/mma_probe tools/mma_probe.cu
 #include <algorithm>
@@ -45,7 +54,8 @@ __device__ __forceinline__ uint16_t bf16_bits(int v) {  // small integers are ex
 constexpr int kSmemA = 0;           // 128 rows x 128 k, two 16 KiB halves (k < 64 | k >= 64)
 constexpr int kSmemB = 32 * 1024;   // up to 256 rows x 128 k, two halves of rows*128 B
 constexpr int kSmemBar = 96 * 1024;
-constexpr int kSmemBytes = kSmemBar + 64;
+constexpr int kSmemScratch = 100 * 1024;  // 2 x 16 KiB landing zone of the interference bulk copies
+constexpr int kSmemBytes = kSmemScratch + 32 * 1024;
 constexpr uint32_t kColD = 0, kColA = 256;
 
 struct ProbeOut {
@@ -53,15 +63,33 @@ struct ProbeOut {
     unsigned long long ns;
 };
 
-// kMode: bit 0 = A from tensor memory, bit 1 = CTA pair
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// random bf16 with |value| in [0.5, 4): random sign, 3 exponents, random mantissa
+__device__ __forceinline__ uint16_t rnd_bf16(uint32_t idx) {
+    const uint32_t h = hash32(idx * 2654435761u + 12345u);
+    const uint32_t sign = (h >> 31) << 15, exp = (126u + (h >> 8) % 3u) << 7, man = h & 0x7fu;
+    return static_cast<uint16_t>(sign | exp | man);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// kMode: bit 0 = A from tensor memory, bit 1 = CTA pair, bit 2 = B MN-major (the kernel's V operand)
 template <int kMode>
-__device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, float* dout) {
+__device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, float* dout, int noise, int rnd,
+                                           const uint8_t* gsrc, float* sink, int pattern) {
     constexpr bool kTS = (kMode & 1) != 0;
     constexpr bool kPair = (kMode & 2) != 0;
+    constexpr bool kBT = (kMode & 4) != 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar = sbase + kSmemBar;
     const uint32_t tmem_ptr = sbase + kSmemBar + 16;
+    const uint32_t bar_noise = bar + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int rows_b = kPair ? N / 2 : N;  // B rows held by this CTA
@@ -69,6 +97,8 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
     if (warp == 0) {
         if (lane == 0) {
             mbar_init(bar, 1);
+            mbar_init(bar + 8, 1);   // interference bulk copies
+            mbar_init(bar + 24, 1);  // pattern 6: per-group commits nobody waits for
             fence_mbar_init();
         }
         __syncwarp();
@@ -85,20 +115,30 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
         const int r = idx >> 7, k = idx & 127;
         const int h = k >> 6, c = (k & 63) >> 3, e = k & 7;
         const uint32_t off = h * (128 * 128) + r * 128 + ((c ^ (r & 7)) * 16) + e * 2;
-        *reinterpret_cast<uint16_t*>(smem + kSmemA + off) = bf16_bits(a_val((int)rank * 128 + r, k));
+        *reinterpret_cast<uint16_t*>(smem + kSmemA + off) =
+            rnd ? rnd_bf16(idx + 7919u * rank) : bf16_bits(a_val((int)rank * 128 + r, k));
     }
     for (int idx = threadIdx.x; idx < rows_b * 128; idx += blockDim.x) {
         const int r = idx >> 7, k = idx & 127;
         const int h = k >> 6, c = (k & 63) >> 3, e = k & 7;
         const uint32_t off = h * (rows_b * 128) + r * 128 + ((c ^ (r & 7)) * 16) + e * 2;
-        *reinterpret_cast<uint16_t*>(smem + kSmemB + off) = bf16_bits(b_val((int)rank * rows_b + r, k));
+        *reinterpret_cast<uint16_t*>(smem + kSmemB + off) =
+            rnd ? rnd_bf16(idx + 104729u * (rank + 2)) : bf16_bits(b_val((int)rank * rows_b + r, k));
+    }
+    if constexpr (kBT) {  // timing only: any 128 keys x (pair: 64, else 128) d columns will do
+        for (int idx = threadIdx.x; idx < 16 * 1024; idx += blockDim.x)
+            reinterpret_cast<uint16_t*>(smem + kSmemB)[idx] = rnd ? rnd_bf16(idx + 31u) : bf16_bits((idx % 5) - 2);
+    }
+    if (pattern != 0) {  // a V-like MN-major operand behind the K-like one (timing only)
+        for (int idx = threadIdx.x; idx < 16 * 1024; idx += blockDim.x)
+            reinterpret_cast<uint16_t*>(smem + kSmemB + 32 * 1024)[idx] = rnd ? rnd_bf16(idx + 77u) : bf16_bits((idx % 5) - 2);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 16);
-    if (kTS && warp < 4) {  // A as the MMA reads it from tensor memory: lane = row, column = k / 2
+    if ((kTS || pattern != 0) && warp < 4) {  // A as the MMA reads it from tensor memory: lane = row, column = k / 2
         const uint32_t t_a = tbase + (static_cast<uint32_t>(warp * 32) << 16) + kColA;
         const int r = (int)rank * 128 + warp * 32 + lane;
 #pragma unroll
@@ -107,7 +147,8 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int k = (q * 32 + i) * 2;
-                v[i] = (uint32_t)bf16_bits(a_val(r, k)) | ((uint32_t)bf16_bits(a_val(r, k + 1)) << 16);
+                v[i] = rnd ? ((uint32_t)rnd_bf16(r * 128 + k) | ((uint32_t)rnd_bf16(r * 128 + k + 1) << 16))
+                           : ((uint32_t)bf16_bits(a_val(r, k)) | ((uint32_t)bf16_bits(a_val(r, k + 1)) << 16));
             }
             tmem_st_32x32b_x32(t_a + q * 32, v);
         }
@@ -118,14 +159,16 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
     else __syncthreads();
     tc_fence_after();
 
-    const uint32_t idesc = umma_idesc_f16(true, kPair ? 256 : 128, N, false);
+    const uint32_t idesc = umma_idesc_f16(true, kPair ? 256 : 128, N, kBT);
     const uint64_t a0 = umma_smem_desc_sw128(sbase + kSmemA, 16, 1024);
-    const uint64_t b0 = umma_smem_desc_sw128(sbase + kSmemB, 16, 1024);
+    const uint64_t b0 = kBT ? umma_smem_desc_sw128(sbase + kSmemB, 16 * 1024, 1024)
+                            : umma_smem_desc_sw128(sbase + kSmemB, 16, 1024);
     auto issue_group = [&](bool first) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t a_off = ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4;
-            const uint32_t b_off = ((k >> 2) * (rows_b * 128) + (k & 3) * 32) >> 4;
+            const uint32_t b_off = kBT ? (uint32_t)((k * 2048) >> 4)
+                                       : (uint32_t)(((k >> 2) * (rows_b * 128) + (k & 3) * 32) >> 4);
             const uint32_t acc = (first && k == 0) ? 0u : 1u;
             if constexpr (kPair) {
                 if constexpr (kTS) umma_ts_2cta(tbase + kColD, tbase + kColA + k * 8, b0 + b_off, idesc, acc);
@@ -134,6 +177,59 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
                 if constexpr (kTS) umma_ts(tbase + kColD, tbase + kColA + k * 8, b0 + b_off, idesc, acc);
                 else umma_ss(tbase + kColD, a0 + a_off, b0 + b_off, idesc, acc);
             }
+        }
+    };
+    // Alternation patterns (N = 128): the attention kernel never runs more than 8 MMAs of one kind in a
+    // row -- S = Q K^T (SS, fresh accumulator) and O += P V (TS, V MN-major) groups alternate.
+    const uint32_t idesc_s = umma_idesc_f16(true, kPair ? 256 : 128, 128, false);
+    const uint32_t idesc_o = umma_idesc_f16(true, kPair ? 256 : 128, 128, true);
+    const uint64_t v0 = umma_smem_desc_sw128(sbase + kSmemB + 32 * 1024, 16 * 1024, 1024);
+    auto mma_s = [&](int k, uint32_t d_col, uint32_t acc) {
+        const uint32_t a_off = ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4;
+        const uint32_t b_off = ((k >> 2) * (rows_b * 128) + (k & 3) * 32) >> 4;
+        if constexpr (kPair) umma_ss_2cta(tbase + d_col, a0 + a_off, b0 + b_off, idesc_s, acc);
+        else umma_ss(tbase + d_col, a0 + a_off, b0 + b_off, idesc_s, acc);
+    };
+    auto mma_o = [&](int k, uint32_t d_col) {
+        if constexpr (kPair) umma_ts_2cta(tbase + d_col, tbase + kColA + k * 8, v0 + ((k * 2048) >> 4), idesc_o, 1u);
+        else umma_ts(tbase + d_col, tbase + kColA + k * 8, v0 + ((k * 2048) >> 4), idesc_o, 1u);
+    };
+    auto issue_pattern = [&]() {
+        if (pattern == 1) {         // S group, then PV group (the kernel's order)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 0, k > 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_o(k, 128);
+        } else if (pattern == 2) {  // the same 16 MMAs interleaved one by one
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                mma_s(k, 0, k > 0);
+                mma_o(k, 128);
+            }
+        } else if (pattern == 3) {  // S groups alternating between two accumulators
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 0, k > 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 128, k > 0);
+        } else if (pattern == 4) {  // S groups into one accumulator, first MMA of each overwrites
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 0, k > 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 0, k > 0);
+        } else if (pattern == 5) {  // PV groups alternating between two accumulators
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_o(k, 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_o(k, 128);
+        } else {                    // 6: S group and PV group, one commit after each (as the kernel does)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_s(k, 0, k > 0);
+            if constexpr (kPair) umma_commit_2cta(bar + 24, 3);
+            else umma_commit(bar + 24);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_o(k, 128);
+            if constexpr (kPair) umma_commit_2cta(bar + 24, 3);
+            else umma_commit(bar + 24);
         }
     };
     auto commit = [&]() {
@@ -173,11 +269,61 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
         t0 = clock64();
         for (int g = 0; g < groups; ++g) {
-            if (elect_one()) issue_group(false);
+            if (elect_one()) {
+                if (pattern == 0) issue_group(false);
+                else issue_pattern();
+            }
             __syncwarp();
         }
         if (elect_one()) commit();
         __syncwarp();
+    }
+    if (warp >= 4 && noise != 0) {
+        // interference agents: run until the commit of the timed MMAs has landed
+        const bool do_math = noise == 1 || noise == 5;
+        const bool do_bulk = (noise == 2 || noise == 3 || noise == 5) && warp == 4;
+        const bool do_ldtm = noise == 4 || noise == 5;
+        const long long pace = noise == 2 ? 0 : 700;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = -0.01f * (float)(lane + i);
+        float acc = 0.f;
+        uint32_t nph = 0;
+        long long next = clock64();
+        const uint32_t t_n = tbase + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 384;
+        for (int iter = 0; iter < (1 << 22); ++iter) {
+            if (mbar_try_wait(bar, phase)) break;
+            if (do_bulk && __shfl_sync(0xffffffffu, (int)(clock64() >= next), 0)) {
+                next += pace;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_noise, 16384);
+                    bulk_g2s(sbase + kSmemScratch + (iter & 1) * 16384, gsrc + ((size_t)(blockIdx.x * 8 + (iter & 7)) << 14),
+                             16384, bar_noise);
+                }
+                __syncwarp();
+                mbar_wait(bar_noise, nph, 7);
+                nph ^= 1;
+            }
+            if (do_ldtm) {
+                uint32_t v[4][32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_n + q * 32, v[q]);
+                tmem_wait_ld();
+                acc += __uint_as_float(v[0][0] ^ v[1][1] ^ v[2][2] ^ v[3][3]);
+            }
+            if (do_math) {
+#pragma unroll
+                for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p = ex2_approx(fmaf(x[i], 0.99f, -0.001f));
+                        acc += p;
+                        x[i] = fmaf(p, -0.01f, x[i] * 0.5f);
+                    }
+                }
+            }
+        }
+        if (sink != nullptr && acc == 123.456f) sink[threadIdx.x] = acc;
     }
     mbar_wait(bar, phase, 2);
     phase ^= 1;
@@ -200,17 +346,21 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(128, 1) probe_1cta(int N, int groups, ProbeOut* out, float* dout) {
-    probe_body<kMode>(N, groups, out, dout);
+__global__ void __launch_bounds__(256, 1)
+probe_1cta(int N, int groups, ProbeOut* out, float* dout, int noise, int rnd, const uint8_t* gsrc, float* sink,
+           int pattern) {
+    probe_body<kMode>(N, groups, out, dout, noise, rnd, gsrc, sink, pattern);
 }
 template <int kMode>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-probe_2cta(int N, int groups, ProbeOut* out, float* dout) {
-    probe_body<kMode>(N, groups, out, dout);
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+probe_2cta(int N, int groups, ProbeOut* out, float* dout, int noise, int rnd, const uint8_t* gsrc, float* sink,
+           int pattern) {
+    probe_body<kMode>(N, groups, out, dout, noise, rnd, gsrc, sink, pattern);
 }
 
 template <class Kern>
-static void run(const char* name, Kern kern, int mode, int N, int n_sm) {
+static void run(const char* name, Kern kern, int mode, int N, int n_sm, int noise = 0, int rnd = 0,
+                int pattern = 0) {
     const bool pair = (mode & 2) != 0;
     const int groups = 2000;
     const int grid = pair ? (n_sm / 2) * 2 : n_sm;
@@ -220,9 +370,14 @@ static void run(const char* name, Kern kern, int mode, int N, int n_sm) {
     CK(cudaMemset(d_out, 0, sizeof(ProbeOut) * grid));
     CK(cudaMalloc(&d_d, sizeof(float) * 2 * 128 * 256));
     CK(cudaMemset(d_d, 0, sizeof(float) * 2 * 128 * 256));
+    static uint8_t* d_src = nullptr;  // source of the interference bulk copies: 128 KiB per CTA
+    if (d_src == nullptr) {
+        CK(cudaMalloc(&d_src, (size_t)160 * 8 * 16384));
+        CK(cudaMemset(d_src, 1, (size_t)160 * 8 * 16384));
+    }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     for (int rep = 0; rep < 2; ++rep) {
-        kern<<<grid, 128, kSmemBytes>>>(N, groups, d_out, d_d);
+        kern<<<grid, 256, kSmemBytes>>>(N, groups, d_out, d_d, noise, rnd, d_src, nullptr, pattern);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             printf("{\"name\": \"%s\", \"N\": %d, \"error\": \"%s\"}\n", name, N, cudaGetErrorString(e));
@@ -246,19 +401,20 @@ static void run(const char* name, Kern kern, int mode, int N, int n_sm) {
                 maxerr = std::max(maxerr, err);
                 bad += err > 1e-3;
             }
+    if (rnd || (mode & 4)) bad = -1;  // timing-only configurations: result not checked
     std::vector<double> per;
     double mhz = 0;
     for (int i = 0; i < grid; i += pair ? 2 : 1) {
-        per.push_back((double)out[i].cycles / (8.0 * groups));
+        per.push_back((double)out[i].cycles / ((pattern ? 16.0 : 8.0) * groups));
         mhz += out[i].ns ? (double)out[i].cycles / out[i].ns * 1e3 : 0;
     }
     std::sort(per.begin(), per.end());
     const double med = per[per.size() / 2];
     const double flop_per_mma = 2.0 * (pair ? 256 : 128) * N * 16;
-    printf("{\"name\": \"%s\", \"mode\": %d, \"N\": %d, \"clk_per_mma_median\": %.1f, \"min\": %.1f, "
+    printf("{\"name\": \"%s\", \"mode\": %d, \"pattern\": %d, \"noise\": %d, \"rnd\": %d, \"N\": %d, \"clk_per_mma_median\": %.1f, \"min\": %.1f, "
            "\"max\": %.1f, \"ideal_clk\": %.1f, \"flop_per_clk_per_sm\": %.0f, \"sm_mhz\": %.0f, "
            "\"mismatches\": %d, \"maxerr\": %.3g}\n",
-           name, mode, N, med, per.front(), per.back(), N / 2.0, flop_per_mma / med / (pair ? 2 : 1),
+           name, mode, pattern, noise, rnd, N, med, per.front(), per.back(), N / 2.0, flop_per_mma / med / (pair ? 2 : 1),
            mhz / per.size(), bad, maxerr);
     fflush(stdout);
     cudaFree(d_out);
@@ -273,7 +429,7 @@ int main(int argc, char** argv) {
     const int only = argc > 1 ? atoi(argv[1]) : -1;
     const int ns[3] = {64, 128, 256};
     for (int mode = 0; mode < 4; ++mode) {
-        if (only >= 0 && mode != only) continue;
+        if (only == -2 || (only >= 0 && mode != only)) continue;
         for (int N : ns) {
             switch (mode) {
                 case 0: run("ss_1cta", probe_1cta<0>, 0, N, n_sm); break;
@@ -283,5 +439,21 @@ int main(int argc, char** argv) {
             }
         }
     }
+    if (only >= 0) return 0;
+    // group alternation (see issue_pattern): clk per MMA averaged over the 16 MMAs of one round
+    for (int rnd = 0; rnd < 2; ++rnd)
+        for (int pattern = 1; pattern <= 6; ++pattern) {
+            run("alt_1cta", probe_1cta<0>, 0, 128, n_sm, 0, rnd, pattern);
+            run("alt_2cta", probe_2cta<2>, 2, 128, n_sm, 0, rnd, pattern);
+        }
+    if (only == -2) return 0;
+    // the attention kernel's four MMA flavours (N = 128) under interference, small-integer and random operands
+    for (int rnd = 0; rnd < 2; ++rnd)
+        for (int noise = 0; noise <= 5; ++noise) {
+            run("ss_1cta", probe_1cta<0>, 0, 128, n_sm, noise, rnd);     // QK^T, one CTA
+            run("ss_2cta", probe_2cta<2>, 2, 128, n_sm, noise, rnd);     // QK^T, CTA pair
+            run("tsT_1cta", probe_1cta<5>, 5, 128, n_sm, noise, rnd);    // P V (V MN-major), one CTA
+            run("tsT_2cta", probe_2cta<7>, 7, 128, n_sm, noise, rnd);    // P V, CTA pair
+        }
     return 0;
 }
