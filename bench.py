@@ -55,6 +55,13 @@ def load_peaks():
     return 1590.0, 1400.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
 
 
+def kernel_name(seq_len):
+    """The kernel the C ABI launches for this sequence length (csrc/fa_api.cu: use_pair_kernel)."""
+    mode = os.environ.get("FA_SM100_MODE", "auto")
+    pair = mode == "pair" or (mode != "single" and seq_len > 256)
+    return "fa::fa_fwd_kernel_pair (2-CTA clusters)" if pair else "fa::fa_fwd_kernel"
+
+
 def load_ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -323,7 +330,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": UNIT,
                          "frac": achieved / burst, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, "
                          f"cuBLAS burst; sustained {sustained})", "frac_of_sustained": achieved / sustained,
-                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": "fa::fa_fwd_kernel",
+                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": kernel_name(N),
                          "kernel_ms": kern_ms, "traffic": load_ncu_traffic()},
             "cpu_baseline": cpu,
             "e2e": e2e,

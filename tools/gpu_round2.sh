@@ -40,6 +40,7 @@ if [ -n "$ABLATE" ]; then
 fi
 if [ -n "$FULL" ]; then
   timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/pytest_gpu_${TAG}.txt 2>&1; tail -2 gpurun_out/pytest_gpu_${TAG}.txt
+  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
   timeout 600 python bench.py --impl reference > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; cut -c1-300 gpurun_out/bench_ref_${TAG}.json
   timeout 600 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; cut -c1-1500 gpurun_out/bench_${TAG}.json
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 5 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
