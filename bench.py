@@ -297,7 +297,7 @@ def main():
                "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
                "path": "fa_fwd_host (C ABI): pinned host Q,K,V -> HBM, kernel, O -> pinned host; "
-                       "batch-pipelined copies inside the timed region"}
+                       "copies pipelined over (batch, head-group) chunks inside the timed region"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1)
     cpu = None

@@ -59,7 +59,7 @@ int fa_fwd_timed(const void* q, const void* k, const void* v, void* o, int batch
                  int64_t stride_head, int dtype, void* stream, float* ms);
 
 /* End-to-end convenience for HOST buffers (contiguous (batch, seq, heads, 128)): copies Q, K, V to
- * device `device`, runs the kernel and copies O back, pipelined over the batch dimension on
+ * device `device`, runs the kernel and copies O back, pipelined over (batch, head-group) chunks of <= 8 MiB per tensor on
  * internal streams; returns after O is complete in host memory.  Pinned host memory makes the
  * copies asynchronous; pageable memory works but serialises.  The reference has no such entry
  * (its operator only accepts CUDA tensors); this exists for end-to-end measurement. */

@@ -308,6 +308,16 @@ def test_host_buffer_entry_equals_device_path():
     assert torch.equal(o_host, o_dev)
 
 
+def test_host_buffer_entry_head_group_chunks():
+    # > 8 MiB per tensor and batch entry: fa_fwd_host splits every batch entry into head groups
+    # (strided 2-D copies, kernel launched on a head slice of the workspace)
+    g = torch.Generator().manual_seed(9)
+    q, k, v = (torch.randn(2, 2048, 24, 128, generator=g).bfloat16().pin_memory() for _ in range(3))
+    o_host = flash_attention.forward_host(q, k, v)
+    o_dev = flash_attention.forward(None, q.to(DEV), k.to(DEV), v.to(DEV)).cpu()
+    assert torch.equal(o_host, o_dev)
+
+
 def test_launch_counter_counts_our_kernel(lib):
     from flash_attention_from_scratch_b200 import _lib
     q, k, v = rand_qkv((1, 256, 1, 128), torch.bfloat16)

@@ -1,0 +1,49 @@
+"""CPU tests of the benchmark tooling that mirrors the reference's tools/benchmark."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+NCU_LOG = '''==PROF== Connected to process 1
+==PROF== Disconnected from process 1
+"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"
+"0","1","python","h","void at::native::vectorized_elementwise_kernel<4>(int)","1","7","(128, 1, 1)","(8, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","us","3.2"
+"1","1","python","h","void fa::fa_fwd_kernel_pair<(bool)1, (bool)0, (bool)0>(CUtensorMap_st, fa::FwdParams)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","us","800"
+"1","1","python","h","void fa::fa_fwd_kernel_pair<(bool)1, (bool)0, (bool)0>(CUtensorMap_st, fa::FwdParams)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","dram__bytes_read.sum","Mbyte","403.0"
+"1","1","python","h","void fa::fa_fwd_kernel_pair<(bool)1, (bool)0, (bool)0>(CUtensorMap_st, fa::FwdParams)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed","%","75.1"
+"2","1","python","h","void fa::fa_fwd_kernel_pair<(bool)1, (bool)0, (bool)0>(CUtensorMap_st, fa::FwdParams)","1","7","(384, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ms","0.9"
+'''
+
+
+def test_ncu_bench_parses_and_summarises_an_ncu_log():
+    nb = _load("tools/benchmark/ncu_bench.py", "ncu_bench")
+    per_kernel = nb.parse_ncu_csv(NCU_LOG)
+    assert list(per_kernel) == ["fa::fa_fwd_kernel_pair<"] or len(per_kernel) == 1
+    (name, metrics), = per_kernel.items()
+    assert "fa_fwd_kernel_pair" in name
+    assert metrics["gpu__time_duration.sum"] == [800e3, 900e3]  # normalised to ns
+    assert metrics["dram__bytes_read.sum"] == [403e6]            # normalised to bytes
+    rows = nb.summarise(per_kernel, seq_len=4096, batch=16)
+    assert len(rows) == 1 and rows[0]["launches"] == 2
+    assert abs(rows[0]["duration"] - 0.85) < 1e-9                # ms
+    assert abs(rows[0]["dram_rd"] - 403.0) < 1e-9                # MB
+    assert abs(rows[0]["tensor"] - 75.1) < 1e-9
+    # the reference's FLOP model B*H*(4 N^2 d + 6 N^2) at (16, 4096, 16, 128)
+    flop = 16 * 16 * (4 * 4096 * 4096 * 128 + 6 * 4096 * 4096)
+    assert abs(rows[0]["tflops"] - flop / 0.85e-3 / 1e12) < 1e-6
+    table = nb.format_table(rows)
+    assert "tensor %" in table and "75.1" in table
+    assert nb.format_table(rows, as_csv=True).count("\n") == 1
+
+
+def test_ncu_bench_ignores_logs_without_a_csv_header():
+    nb = _load("tools/benchmark/ncu_bench.py", "ncu_bench")
+    assert nb.parse_ncu_csv("==PROF== nothing profiled\n") == {}
