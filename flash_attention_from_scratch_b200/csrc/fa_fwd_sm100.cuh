@@ -30,6 +30,8 @@
 //       softmax and epilogue but loads only HALF of every K block (64 keys) and V block (64 of
 //       the 128 d columns): per MMA a CTA reads 6 KiB of smem operands instead of 8, and TMA
 //       writes half as much.
+//   (generation 8 -- S(j+1) prefetched into the exp2 shadow of block j -- was measured, rejected and
+//   removed again: it holds the shared accumulator longer; profiles/r01_g8_sweep.json.)
 //   generation 9  (FA_UNIFORM_WARP, FA_LD_SPLIT; both mappings): the warp index is broadcast with
 //       shfl so that ptxas keeps the MMA warp's counters and descriptors in UNIFORM registers, and
 //       the softmax warps reduce the row max of S[:, :64] while S[:, 64:] is still being fetched.
@@ -103,14 +105,6 @@ static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register
 #define FA_SHARED_S 1         // single-CTA kernel: 1 = generation 6, 0 = generation 4b (see top of file)
 #endif
 constexpr bool kSharedSDefault = FA_SHARED_S != 0;
-#ifndef FA_PREFETCH_S
-#define FA_PREFETCH_S 0       // generation 8 (measured, rejected: 1226 vs 1426 TFLOP/s for CTA pairs,
-                              // profiles/r01_g8_sweep.json): the softmax warpgroup loads the first 96
-                              // columns of S_s(j+1) before the last exp2 fragment of block j and computes
-                              // their row max in that fragment's MUFU shadow.  The early load holds the
-                              // shared S accumulator ~1500 clk longer per block, which stalls the other
-                              // Q tile's S issue; kept for the record, off by default.
-#endif
 #ifndef FA_UNIFORM_WARP
 #define FA_UNIFORM_WARP 1
 #endif
@@ -181,8 +175,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                             const CUtensorMap& tm_v, const CUtensorMap& tm_o,
                                             const FwdParams& prm, const FwdDebug& dbg) {
     constexpr bool kSharedS = kPair || kSharedSDefault;
-    constexpr bool kPrefetch = kSharedS && (FA_PREFETCH_S != 0);
-    constexpr bool kLdSplit = !kPrefetch && !kRagged && (FA_LD_SPLIT != 0);
+    constexpr bool kLdSplit = !kRagged && (FA_LD_SPLIT != 0);
     constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;      // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
@@ -671,8 +664,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             float m_run = -INFINITY;  // running (possibly stale) row max, raw S units
             float l_run = 0.f;        // running row sum of exp2
             const int n_iter = (level >= 4) ? n_blocks : 1;
-            uint32_t sr[4][32];       // this row of S(j); with kPrefetch fragments 0..2 arrive one block early
-            float m012 = -INFINITY;   // kPrefetch: row max of fragments 0..2 of the block about to start
+            uint32_t sr[4][32];       // this thread's row of S(j): 4 fragments of 32 columns
             auto mask_tail = [&](int q_begin, int q_end) {
                 // ragged tail (seq_len % 128 != 0, beyond the reference's contract): TMA zero-filled
                 // the missing K/V rows; their scores are forced to -inf so that P = 0 exactly.
@@ -683,21 +675,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         if (q * 32 + i >= kv_tail) sr[q][i] = 0xff800000u;
                 }
             };
-            if constexpr (kPrefetch) {
-                // first block of the tile: nothing was prefetched
+            for (int j = 0; j < n_iter; ++j, ++g) {
                 wait(s_full(s), g & 1u, 300 + s);
                 tc_fence_after();
-#pragma unroll
-                for (int q = 0; q < 3; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
-                tmem_wait_ld();
-                if (kRagged && n_blocks == 1 && kv_tail != 0) mask_tail(0, 3);
-                m012 = row_max_frags<0, 3>(sr);
-            }
-            for (int j = 0; j < n_iter; ++j, ++g) {
-                if constexpr (!kPrefetch) {
-                    wait(s_full(s), g & 1u, 300 + s);
-                    tc_fence_after();
-                }
                 uint32_t* tr = nullptr;
                 if constexpr (kDebug) {
                     if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
@@ -720,11 +700,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     m_lo = row_max_frags<0, 2>(sr);
                     tmem_wait_ld();
                 } else {
-                    if constexpr (!kPrefetch) {
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
-                    }
-                    tmem_ld_32x32b_x32(t_s + 3 * 32, sr[3]);
+                    for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
                     tmem_wait_ld();
                 }
                 if constexpr (kSharedS) {
@@ -745,8 +722,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     if (tr) tr[1] = clk32();
                 }
                 if (kRagged && j + 1 == n_blocks && kv_tail != 0) {
-                    if constexpr (!kPrefetch) mask_tail(0, 3);  // otherwise masked when (pre)fetched
-                    mask_tail(3, 4);
+                    mask_tail(0, 4);
                 }
 
                 if constexpr (kDebug) {
@@ -764,8 +740,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     mx = 0.f;
                 } else if constexpr (kLdSplit) {
                     mx = fmaxf(m_lo, row_max_frags<2, 2>(sr));
-                } else if constexpr (kPrefetch) {
-                    mx = fmaxf(m012, row_max_frags<3, 1>(sr));
                 } else {
                     mx = row_max_128(sr);
                 }
@@ -814,11 +788,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         for (int i = 0; i < 16; ++i) pk[i] = 0x3c003c00u;
                     } else if (q == 3) {
                         exp_fragment<kBF16, kEmuPairsLast, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
-                        if constexpr (kPrefetch) {
-                            // fragments 0..2 now hold S_s(j+1): their row max shares this basic block
-                            // with the exp2 stream above (ptxas interleaves FMNMX with the MUFU waits)
-                            if (j + 1 < n_iter) m012 = row_max_frags<0, 3>(sr);
-                        }
                     } else {
                         exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     }
@@ -844,21 +813,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         if (lane == 0) arrive_leader(p_full(s));
                         if constexpr (kDebug) {
                             if (tr) tr[3] = clk32();
-                        }
-                    }
-                    if constexpr (kPrefetch) {
-                        if (q == 2 && j + 1 < n_iter) {
-                            // S_s(j+1) was issued while this block's softmax ran: fetch its first 96
-                            // columns into the registers fragments 0..2 of S_s(j) just vacated
-                            wait(s_full(s), (g + 1u) & 1u, 340 + s);
-                            tc_fence_after();
-#pragma unroll
-                            for (int qq = 0; qq < 3; ++qq) tmem_ld_32x32b_x32(t_s + qq * 32, sr[qq]);
-                            tmem_wait_ld();
-                            if (kRagged && j + 2 == n_blocks && kv_tail != 0) mask_tail(0, 3);
-                            if constexpr (kDebug) {
-                                if (tr) tr[7] = clk32();
-                            }
                         }
                     }
                 }

@@ -18,7 +18,6 @@ VARIANTS = {
     "emu8": {"FA_EMU_PAIRS": 8},
     "emu6_4": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 4},
     "noldsplit": {"FA_LD_SPLIT": 0},      # S fetched with one wait, row max afterwards
-    "prefetch": {"FA_PREFETCH_S": 1},     # generation 8 softmax loop (rejected)
     "g4b": {"FA_SHARED_S": 0},            # single-CTA kernel = generation 4b instead of 6
     "emu4_4": {"FA_EMU_PAIRS_LAST": 4},
     "emu2": {"FA_EMU_PAIRS": 2},
