@@ -58,7 +58,7 @@ def load_peaks():
 def kernel_name(seq_len):
     """The kernel the C ABI launches for this sequence length (csrc/fa_api.cu: use_pair_kernel)."""
     mode = os.environ.get("FA_SM100_MODE", "auto")
-    pair = mode == "pair" or (mode != "single" and seq_len > 256)
+    pair = mode == "pair" or (mode != "single" and seq_len > 1024)
     return "fa::fa_fwd_kernel_pair (2-CTA clusters)" if pair else "fa::fa_fwd_kernel"
 
 
@@ -297,7 +297,7 @@ def main():
                "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
                "path": "fa_fwd_host (C ABI): pinned host Q,K,V -> HBM, kernel, O -> pinned host; "
-                       "copies pipelined over (batch, head-group) chunks inside the timed region"}
+                       "batch-pipelined copies inside the timed region"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N == 1)
     cpu = None

@@ -81,8 +81,10 @@ cudaError_t set_smem_attr() {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
 }
 
-// Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  CTA pairs (generation 7) cover 512
-// query rows per work tile, so AUTO uses them when seq_len > 256.
+// Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  Measured with generation 9 on the
+// reference's benchmark shapes (profiles/r01_g9_mode_threshold.txt): single CTAs win up to seq_len 512
+// (+4 %; +21 % at 256), the mappings tie at 1024, CTA pairs win from 2048 on (+1.4 %).
+constexpr int kPairMinSeqLen = 1024;  // AUTO: CTA pairs for seq_len > this
 std::atomic<int> g_mode{[] {
     const char* m = getenv("FA_SM100_MODE");
     if (m != nullptr && strcmp(m, "single") == 0) return FA_MODE_SINGLE;
@@ -93,7 +95,7 @@ bool use_pair_kernel(int seq_len) {
     const int mode = g_mode.load(std::memory_order_relaxed);
     if (mode == FA_MODE_SINGLE) return false;
     if (mode == FA_MODE_PAIR) return true;
-    return seq_len > fa::kQStages * fa::kBlockM;
+    return seq_len > kPairMinSeqLen;
 }
 
 // One-time per-device setup: capability check + opt-in dynamic shared memory
@@ -404,14 +406,7 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
         FA_CUDA(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
         FA_CUDA(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
     }
-    // Chunks of the software pipeline: one batch entry, split further into head groups while a chunk
-    // of one tensor is larger than 8 MiB (strided 2-D copies; the kernel takes the head stride as is).
-    // Smaller chunks shorten the un-overlapped head (first H2D) and tail (last kernel + D2H).
-    int groups = 1;
-    while (per_batch / groups > (8u << 20) && n_heads % (groups * 2) == 0) groups *= 2;
-    const int hg = n_heads / groups;
-    const int n_chunks = batch * groups;
-    while ((int)w.ev_in.size() < n_chunks) {
+    while ((int)w.ev_in.size() < batch) {
         cudaEvent_t a, b;
         FA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         FA_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -419,32 +414,23 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
         w.ev_run.push_back(b);
     }
     const int64_t sh = d_head, sn = (int64_t)n_heads * d_head, sb = (int64_t)seq_len * sn;
-    const size_t pitch = (size_t)sn * 2, width = (size_t)hg * d_head * 2;
-    // H2D(c+1) overlaps kernel(c) overlaps D2H(c-1).
-    for (int c = 0; c < n_chunks; ++c) {
-        const size_t off = per_batch * (size_t)(c / groups) + width * (size_t)(c % groups);
+    // Software pipeline over the batch dimension: H2D(b+1) overlaps kernel(b) overlaps D2H(b-1).
+    for (int b = 0; b < batch; ++b) {
+        const size_t off = per_batch * b;
         const void* src[3] = {q_host, k_host, v_host};
-        for (int t = 0; t < 3; ++t) {
-            if (groups == 1)
-                FA_CUDA(cudaMemcpyAsync((char*)w.d[t] + off, (const char*)src[t] + off, per_batch,
-                                        cudaMemcpyHostToDevice, w.s_in));
-            else
-                FA_CUDA(cudaMemcpy2DAsync((char*)w.d[t] + off, pitch, (const char*)src[t] + off, pitch,
-                                          width, (size_t)seq_len, cudaMemcpyHostToDevice, w.s_in));
-        }
-        FA_CUDA(cudaEventRecord(w.ev_in[c], w.s_in));
-        FA_CUDA(cudaStreamWaitEvent(w.s_run, w.ev_in[c], 0));
+        for (int t = 0; t < 3; ++t)
+            FA_CUDA(cudaMemcpyAsync((char*)w.d[t] + off, (const char*)src[t] + off, per_batch,
+                                    cudaMemcpyHostToDevice, w.s_in));
+        FA_CUDA(cudaEventRecord(w.ev_in[b], w.s_in));
+        FA_CUDA(cudaStreamWaitEvent(w.s_run, w.ev_in[b], 0));
         int rc = fa_fwd((char*)w.d[0] + off, (char*)w.d[1] + off, (char*)w.d[2] + off,
-                        (char*)w.d[3] + off, 1, seq_len, hg, d_head, sb, sn, sh, dtype, w.s_run);
+                        (char*)w.d[3] + off, 1, seq_len, n_heads, d_head, sb, sn, sh, dtype,
+                        w.s_run);
         if (rc != FA_OK) return rc;
-        FA_CUDA(cudaEventRecord(w.ev_run[c], w.s_run));
-        FA_CUDA(cudaStreamWaitEvent(w.s_out, w.ev_run[c], 0));
-        if (groups == 1)
-            FA_CUDA(cudaMemcpyAsync((char*)o_host + off, (char*)w.d[3] + off, per_batch,
-                                    cudaMemcpyDeviceToHost, w.s_out));
-        else
-            FA_CUDA(cudaMemcpy2DAsync((char*)o_host + off, pitch, (char*)w.d[3] + off, pitch, width,
-                                      (size_t)seq_len, cudaMemcpyDeviceToHost, w.s_out));
+        FA_CUDA(cudaEventRecord(w.ev_run[b], w.s_run));
+        FA_CUDA(cudaStreamWaitEvent(w.s_out, w.ev_run[b], 0));
+        FA_CUDA(cudaMemcpyAsync((char*)o_host + off, (char*)w.d[3] + off, per_batch,
+                                cudaMemcpyDeviceToHost, w.s_out));
     }
     FA_CUDA(cudaStreamSynchronize(w.s_out));
     FA_CUDA(cudaStreamSynchronize(w.s_run));

@@ -114,7 +114,7 @@ def forward_timed(kernel_cfg, q, k, v, o=None):
 
 def forward_host(q, k, v, o=None, device: int = 0):
     """End-to-end entry for HOST (ideally pinned) tensors: H2D, kernel, D2H inside the library
-    (fa_fwd_host), pipelined over (batch, head-group) chunks.  Returns the host output tensor."""
+    (fa_fwd_host), pipelined over the batch dimension.  Returns the host output tensor."""
     lib = _lib.load()
     for name, t in (("q", q), ("k", k), ("v", v)):
         if t.is_cuda or not t.is_contiguous():

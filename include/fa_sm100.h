@@ -59,7 +59,7 @@ int fa_fwd_timed(const void* q, const void* k, const void* v, void* o, int batch
                  int64_t stride_head, int dtype, void* stream, float* ms);
 
 /* End-to-end convenience for HOST buffers (contiguous (batch, seq, heads, 128)): copies Q, K, V to
- * device `device`, runs the kernel and copies O back, pipelined over (batch, head-group) chunks of <= 8 MiB per tensor on
+ * device `device`, runs the kernel and copies O back, pipelined over the batch dimension on
  * internal streams; returns after O is complete in host memory.  Pinned host memory makes the
  * copies asynchronous; pageable memory works but serialises.  The reference has no such entry
  * (its operator only accepts CUDA tensors); this exists for end-to-end measurement. */
@@ -85,7 +85,7 @@ int64_t fa_launch_count(void);
 /* Which kernel a launch uses.  The reference selects one of its 85 template instantiations with the
  * kernel_cfg map lookup (flash_attention.cu:59-62); this library has two machine mappings of the same
  * arithmetic and picks by shape:
- *   FA_MODE_AUTO   (default): CTA pairs when seq_len > 256, single CTAs otherwise
+ *   FA_MODE_AUTO   (default): CTA pairs when seq_len > 1024, single CTAs otherwise (measured crossover)
  *   FA_MODE_SINGLE one CTA per SM, work tile = 256 query rows
  *   FA_MODE_PAIR   clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
  * Process-wide; returns the previous mode (or -1 for an invalid argument).  The environment variable
