@@ -55,6 +55,29 @@ def load_peaks():
     return 1590.0, 1400.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under
+    NCCL_DEBUG=VERSION, for one), so fd 1 is pointed at stderr for the rest of the process and the result
+    line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def kernel_name(seq_len):
     """The kernel the C ABI launches for this sequence length (csrc/fa_api.cu: use_pair_kernel)."""
     mode = os.environ.get("FA_SM100_MODE", "auto")
@@ -176,10 +199,11 @@ def run_reference(args, rank, world):
         "e2e": {"value": tflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     # 50 back-to-back launches = 40 ms at the headline.  The board is power-capped under this kernel, so
@@ -340,7 +364,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
