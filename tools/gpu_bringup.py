@@ -67,9 +67,9 @@ def run_one(args):
     kf = k[0, :, 0].float().cpu()
     vf = v[0, :, 0].float().cpu()
     q_img = swizzled_image(q[0, :128, 0].cpu())
-    # CTA pairs (seq_len > 256 unless FA_SM100_MODE says otherwise): CTA 0 holds keys 0..63 of K_0
+    # CTA pairs (seq_len > 1024 unless FA_SM100_MODE says otherwise): CTA 0 holds keys 0..63 of K_0
     mode = os.environ.get("FA_SM100_MODE", "auto")
-    pair = mode == "pair" or (mode != "single" and N > 256)
+    pair = mode == "pair" or (mode != "single" and N > 1024)
     k_img = swizzled_image(k[0, :(64 if pair else 128), 0].cpu())
     ref = None
     if level >= 4:
@@ -158,7 +158,8 @@ def main():
         return
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    guard_lib = os.path.join(ROOT, "flash_attention_from_scratch_b200", "csrc", "libfa_sm100_guard.so")
+    guard_lib = os.environ.get("FA_GUARD_LIB") or os.path.join(
+        ROOT, "flash_attention_from_scratch_b200", "csrc", "libfa_sm100_guard.so")
     guard = {"FA_SM100_LIB": guard_lib} if os.path.exists(guard_lib) else None
     log = []
 
