@@ -61,6 +61,8 @@ constexpr uint32_t kColD = 0, kColA = 256;
 struct ProbeOut {
     unsigned long long cycles;
     unsigned long long ns;
+    unsigned long long first_group;  // one 8-MMA group + commit on an idle tensor pipe: issue -> barrier seen
+    unsigned long long warm_group;   // the same group issued right behind another one (minus that one's 8 MMAs)
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
@@ -237,8 +239,10 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
         else umma_commit(bar);
     };
     uint32_t phase = 0;
-    // ---- 1. one K = 128 product, checked on the host ----
+    // ---- 1. one K = 128 product, checked on the host; its latency on an idle pipe is recorded ----
+    unsigned long long g0 = 0, g1 = 0;
     if (warp == 0 && rank == 0) {
+        g0 = clock64();
         if (elect_one()) {
             issue_group(true);
             commit();
@@ -247,6 +251,10 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
     }
     mbar_wait(bar, phase, 1);
     phase ^= 1;
+    if (warp == 0 && rank == 0) {
+        g1 = clock64();
+        if (lane == 0) out[blockIdx.x].first_group = g1 - g0;
+    }
     tc_fence_after();
     if (dout != nullptr && blockIdx.x < 2 && warp < 4) {
         const uint32_t t_d = tbase + (static_cast<uint32_t>(warp * 32) << 16) + kColD;
@@ -263,6 +271,28 @@ __device__ __forceinline__ void probe_body(int N, int groups, ProbeOut* out, flo
     if constexpr (kPair) cluster_sync();
     else __syncthreads();
     tc_fence_after();
+    // ---- 1b. the same group issued right behind another one (pipe and operand path warm) ----
+    if (pattern == 0) {
+        if (warp == 0 && rank == 0) {
+            g0 = clock64();
+            if (elect_one()) {
+                issue_group(false);
+                issue_group(false);
+                commit();
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, phase, 3);
+        phase ^= 1;
+        if (warp == 0 && rank == 0) {
+            g1 = clock64();
+            if (lane == 0) out[blockIdx.x].warm_group = g1 - g0;
+        }
+        tc_fence_before();
+        if constexpr (kPair) cluster_sync();
+        else __syncthreads();
+        tc_fence_after();
+    }
     // ---- 2. `groups` x 8 MMAs back to back, one commit at the end ----
     unsigned long long t0 = 0, t1 = 0, n0 = 0, n1 = 0;
     if (warp == 0 && rank == 0) {
@@ -402,20 +432,24 @@ static void run(const char* name, Kern kern, int mode, int N, int n_sm, int nois
                 bad += err > 1e-3;
             }
     if (rnd || (mode & 4)) bad = -1;  // timing-only configurations: result not checked
-    std::vector<double> per;
+    std::vector<double> per, first, warm;
     double mhz = 0;
     for (int i = 0; i < grid; i += pair ? 2 : 1) {
         per.push_back((double)out[i].cycles / ((pattern ? 16.0 : 8.0) * groups));
+        first.push_back((double)out[i].first_group);
+        warm.push_back((double)out[i].warm_group);
         mhz += out[i].ns ? (double)out[i].cycles / out[i].ns * 1e3 : 0;
     }
     std::sort(per.begin(), per.end());
+    std::sort(first.begin(), first.end());
+    std::sort(warm.begin(), warm.end());
     const double med = per[per.size() / 2];
     const double flop_per_mma = 2.0 * (pair ? 256 : 128) * N * 16;
     printf("{\"name\": \"%s\", \"mode\": %d, \"pattern\": %d, \"noise\": %d, \"rnd\": %d, \"N\": %d, \"clk_per_mma_median\": %.1f, \"min\": %.1f, "
            "\"max\": %.1f, \"ideal_clk\": %.1f, \"flop_per_clk_per_sm\": %.0f, \"sm_mhz\": %.0f, "
-           "\"mismatches\": %d, \"maxerr\": %.3g}\n",
+           "\"mismatches\": %d, \"maxerr\": %.3g, \"group8_latency_cold\": %.0f, \"two_groups_latency\": %.0f}\n",
            name, mode, pattern, noise, rnd, N, med, per.front(), per.back(), N / 2.0, flop_per_mma / med / (pair ? 2 : 1),
-           mhz / per.size(), bad, maxerr);
+           mhz / per.size(), bad, maxerr, first[first.size() / 2], warm[warm.size() / 2]);
     fflush(stdout);
     cudaFree(d_out);
     cudaFree(d_d);
