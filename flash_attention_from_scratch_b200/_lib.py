@@ -30,6 +30,7 @@ SYMBOLS = {
     "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
     "fa_launch_count": (_L, []),
     "fa_set_kernel_mode": (_I, [_I]),
+    "fa_set_thread_kernel_mode": (_I, [_I]),
     "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32), _P]),
 }
 
@@ -75,6 +76,27 @@ def set_kernel_mode(mode: int) -> int:
     if prev < 0:
         raise ValueError(f"invalid kernel mode {mode}")
     return prev
+
+
+class thread_kernel_mode:
+    """Context manager: machine mapping for launches of the calling thread only
+    (include/fa_sm100.h: fa_set_thread_kernel_mode).  `mode` 0 / None leaves the choice alone."""
+
+    def __init__(self, mode):
+        self.mode = int(mode) if mode else 0
+        self.prev = -1
+
+    def __enter__(self):
+        if self.mode in (MODE_SINGLE, MODE_PAIR):
+            self.prev = int(load().fa_set_thread_kernel_mode(self.mode))
+        elif self.mode != 0:
+            raise ValueError(f"invalid cta_group {self.mode} (0 = auto, 1 = single CTAs, 2 = CTA pairs)")
+        return self
+
+    def __exit__(self, *exc):
+        if self.mode in (MODE_SINGLE, MODE_PAIR):
+            load().fa_set_thread_kernel_mode(self.prev)
+        return False
 
 
 def kernel_info() -> dict:

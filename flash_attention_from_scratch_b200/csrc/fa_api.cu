@@ -91,8 +91,9 @@ std::atomic<int> g_mode{[] {
     if (m != nullptr && strcmp(m, "pair") == 0) return FA_MODE_PAIR;
     return FA_MODE_AUTO;
 }()};
+thread_local int t_mode = -1;  // fa_set_thread_kernel_mode: per-thread override, -1 = none
 bool use_pair_kernel(int seq_len) {
-    const int mode = g_mode.load(std::memory_order_relaxed);
+    const int mode = t_mode >= 0 ? t_mode : g_mode.load(std::memory_order_relaxed);
     if (mode == FA_MODE_SINGLE) return false;
     if (mode == FA_MODE_PAIR) return true;
     return seq_len > kPairMinSeqLen;
@@ -283,6 +284,13 @@ int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed
 int fa_set_kernel_mode(int mode) {
     if (mode != FA_MODE_AUTO && mode != FA_MODE_SINGLE && mode != FA_MODE_PAIR) return -1;
     return g_mode.exchange(mode, std::memory_order_relaxed);
+}
+
+int fa_set_thread_kernel_mode(int mode) {
+    if (mode != -1 && mode != FA_MODE_AUTO && mode != FA_MODE_SINGLE && mode != FA_MODE_PAIR) return -2;
+    const int prev = t_mode;
+    t_mode = mode;
+    return prev;
 }
 
 int fa_device_info(int device, int* n_sms, int* smem_optin_bytes, int* compute_capability) {

@@ -85,6 +85,9 @@ class FlashForwardKernelConfig:
     V_mma_load_K_tiles: int = 0
     mma_double_buffer_loads: bool = False
     optimized_softmax: bool = True
+    # Blackwell knob (not in the reference): machine mapping of the sm_100a kernel.  0 = the library's
+    # choice by sequence length, 1 = single CTAs (tcgen05 cta_group::1), 2 = 2-CTA clusters (cta_group::2).
+    cta_group: int = 0
 
     def __str__(self) -> str:
         return self.short_form()
@@ -98,6 +101,8 @@ class FlashForwardKernelConfig:
             feats.append("buffer")
         if self.optimized_softmax:
             feats.append("opt_softmax")
+        if self.cta_group:
+            feats.append(f"cta{self.cta_group}")
         head = ""
         if include_tup:
             d = f"{self.d_head}, " if include_d_head else ""
@@ -105,7 +110,7 @@ class FlashForwardKernelConfig:
         return head + "+".join(feats)
 
     def kernel_name(self) -> str:
-        return "fa_fwd_kernel"
+        return "fa_fwd_kernel_pair" if self.cta_group == 2 else "fa_fwd_kernel"
 
     def attn_flop(self, n_samples: int, n_heads: int, seq_len: int) -> int:
         return calc_self_attn_flop(n_samples, n_heads, seq_len, self.d_head)
@@ -132,7 +137,8 @@ def parse_kernel_name_into_config(text: str) -> FlashForwardKernelConfig:
         n_warps=int(n_warps), async_copy="async" in feats, eager_load_blocks="eager" in feats,
         swizzled="swizzled" in feats, Q_mma_load_K_tiles=qt, K_mma_load_K_tiles=kt,
         V_mma_load_K_tiles=vt, mma_double_buffer_loads="buffer" in feats,
-        optimized_softmax="opt_softmax" in feats)
+        optimized_softmax="opt_softmax" in feats,
+        cta_group=next((int(f[3:]) for f in feats if f in ("cta1", "cta2")), 0))
 
 
 def get_kernels_to_build():
@@ -142,15 +148,21 @@ def get_kernels_to_build():
 
 
 def get_autotuning_kernel_configs(dtypes=(DType.BF16, DType.FP16)):
-    return [FlashForwardKernelConfig(dtype=dt) for dt in dtypes]
+    """The tuning grid of the sm_100a kernel: both machine mappings per dtype (the reference's grid of
+    Ampere tile knobs, kernel_configs.py:364-455, has no meaning here).  Build-time knobs (exp2 emulation
+    fraction, K/V ring depth, register split) are swept with tools/build_variants.py instead."""
+    return [FlashForwardKernelConfig(dtype=dt, cta_group=cg) for dt in dtypes for cg in (1, 2)]
 
 
 def get_kernel_configs(kernels_key: str = ""):
     """Same `KERNELS` env UX as the reference (kernel_configs.py:465-485); every key maps onto the
-    per-dtype kernels; "B_r,B_c" keeps only matching tile sizes (i.e. "128,128")."""
+    per-dtype kernels except "tune" (both machine mappings per dtype); "B_r,B_c" keeps only matching
+    tile sizes (i.e. "128,128")."""
     if kernels_key == "":
         kernels_key = os.environ.get("KERNELS", "all")
-    if kernels_key.startswith("prog") or kernels_key in ("all", "tune"):
+    if kernels_key == "tune":
+        return get_autotuning_kernel_configs()
+    if kernels_key.startswith("prog") or kernels_key == "all":
         return get_kernels_to_build()
     if "," in kernels_key:
         b_r, b_c = map(int, kernels_key.split(","))

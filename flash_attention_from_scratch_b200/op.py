@@ -90,7 +90,7 @@ def forward(kernel_cfg, q, k, v, o=None):
     """O = softmax(Q K^T / sqrt(d)) V; asynchronous on the current stream; returns O."""
     lib = _lib.load()
     o = _prepare(kernel_cfg, q, k, v, o)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _lib.thread_kernel_mode(getattr(kernel_cfg, "cta_group", 0)):
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.fa_fwd(*_args(q, k, v, o), stream)
     if rc != 0:
@@ -104,7 +104,7 @@ def forward_timed(kernel_cfg, q, k, v, o=None):
     lib = _lib.load()
     o = _prepare(kernel_cfg, q, k, v, o)
     ms = C.c_float(0.0)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _lib.thread_kernel_mode(getattr(kernel_cfg, "cta_group", 0)):
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.fa_fwd_timed(*_args(q, k, v, o), stream, C.byref(ms))
     if rc != 0:

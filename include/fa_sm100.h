@@ -95,6 +95,12 @@ int64_t fa_launch_count(void);
 #define FA_MODE_PAIR 2
 int fa_set_kernel_mode(int mode);
 
+/* Same choice for the CALLING THREAD only; overrides the process-wide mode until reset with -1.
+ * This is what a per-call `kernel_cfg` selection maps to (the reference looks its kernel up per call,
+ * flash_attention.cu:59-62): the Python operator brackets a launch with it when kernel_cfg.cta_group is
+ * 1 (single CTAs) or 2 (CTA pairs).  Returns the previous override (-1 = none), -2 for a bad argument. */
+int fa_set_thread_kernel_mode(int mode);
+
 /* Bring-up entry: runs the debug instantiation with explicit descriptor knobs and a dump buffer
  * (see FwdDebug in csrc/fa_fwd_sm100.cuh).  knobs[7] = bring-up level (1 setup only, 2 TMA,
  * 3 QK^T, >= 4 everything; knobs[0..6] are ignored); `dump` and `diag` should be host-mapped

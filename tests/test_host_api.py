@@ -103,6 +103,14 @@ def test_kernel_configs_surface():
     for c in cfgs:
         assert parse_kernel_name_into_config(str(c)) == c
     assert get_kernel_configs("128,128") == cfgs and get_kernel_configs("64,64") == []
+    # the Blackwell tuning grid (KERNELS=tune): both machine mappings per dtype, round-tripping names
+    tune = get_kernel_configs("tune")
+    assert sorted((c.dtype, c.cta_group) for c in tune) == sorted(
+        (dt, cg) for dt in (DType.FP16, DType.BF16) for cg in (1, 2))
+    for c in tune:
+        assert f"cta{c.cta_group}" in str(c) and parse_kernel_name_into_config(str(c)) == c
+    assert tune[0].kernel_name() in ("fa_fwd_kernel", "fa_fwd_kernel_pair")
+    assert all(c.cta_group == 0 and "cta" not in str(c) for c in cfgs)
     # FLOP model of the reference README (kernel_configs.py:102-103)
     assert calc_self_attn_flop(4, 32, 4096, 128) == 4 * 32 * (4 * 4096**2 * 128 + 6 * 4096**2)
     assert FlashForwardKernelConfig(dtype=DType.BF16).total_flop(4, 32, 4096) == 4 * 4 * 32 * 4096**2 * 128

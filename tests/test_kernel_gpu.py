@@ -92,6 +92,27 @@ def test_both_machine_mappings(mode, dtype, B, N, H):
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=atol)
 
 
+def test_kernel_cfg_selects_the_machine_mapping_per_call():
+    """kernel_cfg.cta_group = 1 / 2 picks single CTAs / CTA pairs for that call only (thread-local
+    override in the library); every config of the tuning grid reproduces the AUTO result."""
+    from flash_attention_from_scratch_b200 import _lib
+    from flash_helpers.kernel_configs import get_kernel_configs
+    q, k, v = rand_qkv((2, 1536, 6, 128), torch.bfloat16, seed=77)
+    auto = flash_attention.forward(cfg_for(torch.bfloat16), q, k, v)
+    n = 0
+    for kcfg in get_kernel_configs("tune"):
+        if kcfg.dtype.to_torch_dtype() != torch.bfloat16:
+            continue
+        out, ms = flash_attention.forward_timed(kcfg, q, k, v)
+        assert ms > 0
+        # same arithmetic in both mappings; equality is not promised across them, closeness is
+        torch.testing.assert_close(out.float(), auto.float(), rtol=0, atol=2e-3)
+        n += 1
+    assert n == 2
+    lib = _lib.load()
+    assert lib.fa_set_thread_kernel_mode(-1) == -1  # the override was reset after every call
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_reference_suite_shape_and_criterion(dtype):
     # py/flash_helpers/test/test.py:19-61: (16, 2048, 16, 128), every config of get_kernels_to_build()

@@ -80,7 +80,7 @@ def main():
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     rows = []
     for d_head in d_heads:
-        for cfg in get_kernel_configs("all"):
+        for cfg in get_kernel_configs():  # KERNELS env: all (default) | tune (both machine mappings) | "128,128"
             dt = cfg.dtype.to_torch_dtype()
             per_seq = []
             for n in seq_lens:
