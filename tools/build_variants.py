@@ -1,6 +1,10 @@
 #!/usr/bin/env python
 """Builds tuning variants of libfa_sm100.so (different -D knobs) into csrc/variants/ so one GPU
-round trip can time all of them (tools/sweep_variants.py).  Development aid."""
+round trip can time all of them (tools/sweep_variants.py).  Development aid.
+
+    python tools/build_variants.py base emu6            # csrc/variants/libfa_{base,emu6}.so
+    python tools/build_variants.py psmem --guard        # + libfa_guard_psmem.so for tools/gpu_variant_check.sh
+"""
 import os
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -13,6 +17,7 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 VARIANTS = {
     # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
     "base": {},
+    "psmem": {"FA_P_SMEM": 1},            # generation 11 candidate (pair): P through smem, S per Q tile -- untested
     "nouwarp": {"FA_UNIFORM_WARP": 0},    # warp index straight from threadIdx (generation 7 code shape)
     "emu6": {"FA_EMU_PAIRS": 6},
     "emu8": {"FA_EMU_PAIRS": 8},
@@ -28,13 +33,18 @@ VARIANTS = {
 
 
 def main():
-    names = sys.argv[1:] or list(VARIANTS)
+    args = [a for a in sys.argv[1:] if a != "--guard"]
+    guard = "--guard" in sys.argv[1:]  # also build libfa_guard_<name>.so (bounded mbarrier spins that trap)
+    names = args or list(VARIANTS)
     out_dir = fa_build.CSRC / "variants"
     out_dir.mkdir(exist_ok=True)
 
     def one(name):
         flags = tuple(f"-D{k}={v}" for k, v in VARIANTS[name].items())
         path = fa_build.build(force=True, extra_flags=flags, out=out_dir / f"libfa_{name}.so")
+        if guard:
+            fa_build.build(force=True, extra_flags=flags + ("-DFA_HANG_GUARD=1",),
+                           out=out_dir / f"libfa_guard_{name}.so")
         return name, path
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

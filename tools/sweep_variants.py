@@ -22,6 +22,8 @@ def main():
     rows = []
     for lib in sorted(vdir.glob("libfa_*.so")):
         name = lib.stem[len("libfa_"):]
+        if name.startswith("guard_"):  # bring-up builds (tools/build_variants.py --guard), not for timing
+            continue
         if args.only and name not in args.only.split(","):
             continue
         for mode in args.modes.split(","):
