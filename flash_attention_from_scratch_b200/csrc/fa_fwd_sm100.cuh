@@ -455,6 +455,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             if constexpr (kPSmem) {
                 // ------- generation 11 candidate: one S accumulator per Q tile, P through smem -------
                 // Issue order per work tile:  S_0(0) S_1(0) | S_0(j+1) PV_0(j) S_1(j+1) PV_1(j) | ...
+                // (FA_P_SMEM=2:                S_0(0) S_1(0) | S_0(j+1) S_1(j+1) PV_0(j) PV_1(j) | ...)
                 // S_s(j+1) only waits for warpgroup s to have read S_s(j) out (start of ITS block j), so
                 // it retires ~1000 clk before it is needed; nothing links the two Q tiles any more.
                 int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
@@ -513,10 +514,17 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     issue_s2(0, 0);
                     issue_s2(1, 0);
                     for (int j = 0; level >= 4 && j < n_blocks; ++j) {
-                        if (j + 1 < n_blocks) issue_s2(0, j + 1);
-                        issue_o2(0, j);
-                        if (j + 1 < n_blocks) issue_s2(1, j + 1);
-                        issue_o2(1, j);
+                        if constexpr (FA_P_SMEM == 2) {  // both S first: S_1(j+1) gets ~1100 clk of slack
+                            if (j + 1 < n_blocks) issue_s2(0, j + 1);
+                            if (j + 1 < n_blocks) issue_s2(1, j + 1);
+                            issue_o2(0, j);
+                            issue_o2(1, j);
+                        } else {
+                            if (j + 1 < n_blocks) issue_s2(0, j + 1);
+                            issue_o2(0, j);
+                            if (j + 1 < n_blocks) issue_s2(1, j + 1);
+                            issue_o2(1, j);
+                        }
                     }
                     base += 2 * n_blocks;
                     g0 += (uint32_t)n_blocks;

@@ -18,6 +18,7 @@ VARIANTS = {
     # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
     "base": {},
     "psmem": {"FA_P_SMEM": 1},            # generation 11 candidate (pair): P through smem, S per Q tile -- untested
+    "psmem2": {"FA_P_SMEM": 2},           # same, both S of a block issued before the two PV -- untested
     "nouwarp": {"FA_UNIFORM_WARP": 0},    # warp index straight from threadIdx (generation 7 code shape)
     "emu6": {"FA_EMU_PAIRS": 6},
     "emu8": {"FA_EMU_PAIRS": 8},
