@@ -111,8 +111,8 @@ constexpr bool kSharedSDefault = FA_SHARED_S != 0;
                               // P travels through shared memory (A operand of an SS MMA) instead of tensor
                               // memory, which frees 128 TMEM columns for one S accumulator PER Q tile and
                               // removes the serial chain through the shared accumulator.
-                              // Shared memory: K/V ring 4 x 16 KiB, P tiles 2 x 32 KiB in the other half
-                              // of the old ring.  Tensor memory: [0,128) S_0  [128,256) S_1  O as before.
+                              // Shared memory: K/V ring 6 x 16 KiB, P tiles 2 x 32 KiB behind it (the O
+                              // staging buffers alias them).  Tensor memory: [0,128) S_0  [128,256) S_1.
 #endif
 #ifndef FA_UNIFORM_WARP
 #define FA_UNIFORM_WARP 1
@@ -186,13 +186,20 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     constexpr bool kSharedS = kPair || kSharedSDefault;
     constexpr bool kLdSplit = !kRagged && (FA_LD_SPLIT != 0);
     constexpr bool kPSmem = kPair && (FA_P_SMEM != 0);
-    constexpr int kStages = kPSmem ? 4 : kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
+    constexpr int kStages = kPSmem ? 6 : kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
     constexpr uint32_t kArrivals = kPair ? 8u : 4u;  // softmax warps arriving on one barrier
     constexpr int kRowsPerTile = (kPair ? 2 : 1) * kQStages * kBlockM;
-    // kPSmem: P_s tiles ([2 key halves][128 rows][128 B], 128B swizzle, like Q) behind the 4-slot ring
-    constexpr int kSmemP = kSmemKV + 4 * (kTileBytes / 2);
+    // kPSmem: P_s tiles ([2 key halves][128 rows][128 B], 128B swizzle, like Q) behind a 6-slot ring; they
+    // end where the O staging buffers end.  The epilogue of warpgroup s stages O in the first 16 KiB of
+    // P_s: the last PV_s has read it (pv_done is waited first) and the next tile's P_s is written by the
+    // same warpgroup only after its TMA stores have read the staging buffer.
+    constexpr int kSmemP = kSmemKV + 6 * (kTileBytes / 2);
+    static_assert(!kPSmem || kSmemP + kQStages * kTileBytes == kSmemStage + kQStages * kHalfBytes,
+                  "P tiles must fit between the 6-slot ring and the barriers");
+    constexpr int kSmemO = kPSmem ? kSmemP : kSmemStage;                   // O staging of Q tile 0 ...
+    constexpr int kSmemOStride = kPSmem ? kTileBytes : kHalfBytes;         // ... and the step to tile 1
     auto col_s = [](int s) -> uint32_t {  // tensor-memory column of the S accumulator of Q tile s
         return kPSmem ? static_cast<uint32_t>(s) * 128u : tmem_col_s<kPair || kSharedSDefault>(s);
     };
@@ -961,8 +968,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 // buffer, written with the TMA 128B swizzle: 16-byte chunk c of row r lives at
                 // chunk (c ^ (r & 7)) of that row.
                 const TileCoord tc = coord_of(tile);
-                uint8_t* stage_row = smem_gen + kSmemStage + s * kHalfBytes + row * 128;
-                const uint32_t stage_u32 = smem_base + kSmemStage + s * kHalfBytes;
+                uint8_t* stage_row = smem_gen + kSmemO + s * kSmemOStride + row * 128;
+                const uint32_t stage_u32 = smem_base + kSmemO + s * kSmemOStride;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
