@@ -47,3 +47,14 @@ def test_ncu_bench_parses_and_summarises_an_ncu_log():
 def test_ncu_bench_ignores_logs_without_a_csv_header():
     nb = _load("tools/benchmark/ncu_bench.py", "ncu_bench")
     assert nb.parse_ncu_csv("==PROF== nothing profiled\n") == {}
+
+
+def test_sanity_check_tool_imports_and_lists_its_flags():
+    # tools/debug/sanity_check.py mirrors the reference's flags (--small --diff --kernel)
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "debug", "sanity_check.py"), "--help"],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-500:]
+    for flag in ("--small", "--diff", "--kernel"):
+        assert flag in p.stdout
