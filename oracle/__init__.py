@@ -12,6 +12,7 @@ against them bit for bit (py_flash_attention) / to fp32 round-off (block-wise).
 """
 from .attention_ref import (  # noqa: F401
     blockwise_kernel_ref,
+    ex2_emulated_ref,
     py_flash_attention,
     reference_pass_criterion,
     sdpa_ref,

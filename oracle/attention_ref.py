@@ -49,13 +49,39 @@ def sdpa_ref(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, fp32: bool = Fal
     return o.to(dt).contiguous()
 
 
+def ex2_emulated_ref(x: torch.Tensor) -> torch.Tensor:
+    """Bit-level restatement (fp32 torch ops) of the kernel's FMA-pipe exp2
+    (flash_attention_from_scratch_b200/csrc/ptx_sm100.cuh: ex2_emulated_x2), which replaces the
+    MUFU `ex2.approx` of the reference (softmax.cuh:51-64 under --use_fast_math) for a quarter of the
+    elements: clamp at -127, floor via the round-down magic-number add, degree-3 polynomial for
+    2^frac, integer part added into the exponent field."""
+    import numpy as np
+
+    xf = x.detach().to(torch.float32).cpu().numpy().astype(np.float32)
+    xf = np.maximum(xf, np.float32(-127.0))
+    # t = x + (2^23 + 2^22) rounded DOWN: exact in float64, then rounded toward -inf to fp32
+    t64 = xf.astype(np.float64) + 12582912.0
+    t = t64.astype(np.float32)
+    t = np.where(t.astype(np.float64) > t64, np.nextafter(t, np.float32(-np.inf)), t).astype(np.float32)
+    r = (t - np.float32(12582912.0)).astype(np.float32)          # floor(x) as float
+    f = (xf - r).astype(np.float32)                              # fractional part in [0, 1)
+    fma = lambda a, b, c_: (a.astype(np.float64) * b.astype(np.float64) + np.float64(c_)).astype(np.float32)  # noqa: E731
+    p = fma(np.full_like(f, np.float32(0.07706724)), f, np.float32(0.22764498))
+    p = fma(p, f, np.float32(0.69511664))
+    p = fma(p, f, np.float32(1.0))
+    bits = p.view(np.int32) + (t.view(np.int32) << 23)           # 2^floor(x) into the exponent
+    return torch.from_numpy(bits.view(np.float32).copy()).to(x.device)
+
+
 def blockwise_kernel_ref(q, k, v, block: int = 128, reverse: bool = False,
-                         rescale_threshold: float = 0.0, return_stats: bool = False):
+                         rescale_threshold: float = 0.0, return_stats: bool = False,
+                         emulated_pairs: int = 0):
     """Block-wise online-softmax attention with the kernel's rounding points.
 
     reverse=True walks KV blocks N/B_c-1 .. 0 like the reference (forward_kernel.cuh:142,180);
     the B200 kernel walks 0 .. N/B_c-1.  rescale_threshold=0 rescales on every max increase
-    (reference, softmax.cuh:37-49); 8.0 restates the B200 kernel's lazy rescale.
+    (reference, softmax.cuh:37-49); 8.0 restates the B200 kernel's lazy rescale.  emulated_pairs=4
+    additionally restates its polynomial exp2 on a quarter of the elements (production setting).
     """
     B, N, H, D = q.shape
     dt = q.dtype
@@ -82,6 +108,17 @@ def blockwise_kernel_ref(q, k, v, block: int = 128, reverse: bool = False,
             m_new = torch.where(take, m_blk, m)
             alpha = torch.where(take, torch.exp2((m - m_blk) * c), torch.ones_like(l))
         p32 = torch.exp2(s * c - m_new * c)                          # softmax.cuh:51-64
+        if emulated_pairs:
+            # the kernel computes `emulated_pairs` of every 16 (even, odd) key pairs of the first three
+            # 32-key fragments of a block with the polynomial (softmax_sm100.cuh: emulate_pair)
+            xs = s * c - m_new * c
+            sel = torch.zeros(block, dtype=torch.bool)
+            for frag in range(min(3, block // 32)):
+                for pair in range(16):
+                    if (pair * emulated_pairs) % 16 < emulated_pairs:
+                        sel[frag * 32 + 2 * pair: frag * 32 + 2 * pair + 2] = True
+            sel = sel[: xs.shape[-1]]
+            p32 = torch.where(sel, ex2_emulated_ref(xs), p32)
         l = alpha * l + p32.sum(dim=-1, keepdim=True)                # un-rounded fp32 sum, :66-83
         o = alpha * o + p32.to(dt).float() @ vf[:, :, j0:j0 + block]  # P rounded RN to 16 bit
         m = m_new
