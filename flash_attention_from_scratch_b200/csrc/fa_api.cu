@@ -19,6 +19,7 @@
 
 #include "../../include/fa_sm100.h"
 #include "fa_fwd_sm100.cuh"
+#include "fa_fwd_pp_sm100.cuh"
 
 namespace {
 
@@ -77,8 +78,11 @@ cudaError_t set_smem_attr() {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          fa::kSmemLaunchBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fa::fa_fwd_kernel_pair<kBF16, kDebug, kRagged>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
+    e = cudaFuncSetAttribute(fa::fa_fwd_kernel_pair<kBF16, kDebug, kRagged>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, fa::kSmemLaunchBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fa::pp::fa_fwd_kernel_pp<kBF16, kDebug, kRagged>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, fa::pp::kSmemLaunchBytes);
 }
 
 // Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  Measured with generation 9 on the
@@ -89,14 +93,14 @@ std::atomic<int> g_mode{[] {
     const char* m = getenv("FA_SM100_MODE");
     if (m != nullptr && strcmp(m, "single") == 0) return FA_MODE_SINGLE;
     if (m != nullptr && strcmp(m, "pair") == 0) return FA_MODE_PAIR;
+    if (m != nullptr && (strcmp(m, "pingpong") == 0 || strcmp(m, "pp") == 0)) return FA_MODE_PINGPONG;
     return FA_MODE_AUTO;
 }()};
 thread_local int t_mode = -1;  // fa_set_thread_kernel_mode: per-thread override, -1 = none
-bool use_pair_kernel(int seq_len) {
+int pick_kernel(int seq_len) {  // FA_MODE_SINGLE, FA_MODE_PAIR or FA_MODE_PINGPONG
     const int mode = t_mode >= 0 ? t_mode : g_mode.load(std::memory_order_relaxed);
-    if (mode == FA_MODE_SINGLE) return false;
-    if (mode == FA_MODE_PAIR) return true;
-    return seq_len > kPairMinSeqLen;
+    if (mode != FA_MODE_AUTO) return mode;
+    return seq_len > kPairMinSeqLen ? FA_MODE_PAIR : FA_MODE_SINGLE;
 }
 
 // One-time per-device setup: capability check + opt-in dynamic shared memory
@@ -138,6 +142,12 @@ int init_device(int dev) {
         if (e == cudaSuccess) e = set_smem_attr<false, false, true>();
         if (e == cudaSuccess) e = set_smem_attr<true, true, true>();
         if (e == cudaSuccess) e = set_smem_attr<false, true, true>();
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fa::pp::fa_fwd_kernel_pp<true, true, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, fa::pp::kSmemLaunchBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fa::pp::fa_fwd_kernel_pp<false, true, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, fa::pp::kSmemLaunchBytes);
         if (cur != dev && cur >= 0) cudaSetDevice(cur);
         if (e != cudaSuccess) {
             st.status = FA_ERR_LAUNCH;
@@ -205,8 +215,10 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     int rc = init_device(dev);
     if (rc != FA_OK) return rc;
 
-    const bool pair = use_pair_kernel(p.N);
-    const int rows_per_tile = (pair ? 2 : 1) * fa::kQStages * fa::kBlockM;
+    const int kern = pick_kernel(p.N);
+    const bool pingpong = kern == FA_MODE_PINGPONG;
+    const bool pair = kern != FA_MODE_SINGLE;  // clusters of two CTAs
+    const int rows_per_tile = pingpong ? 2 * fa::kBlockM : (pair ? 2 : 1) * fa::kQStages * fa::kBlockM;
     CUtensorMap tq, tk, tv, to;
     if ((rc = make_tensor_map(&tq, p.q, p)) != FA_OK) return rc;
     // a CTA of a pair loads 64 keys of every K block
@@ -233,7 +245,20 @@ int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
     // one instantiation per (dtype, ragged tail?); the debug build always carries the masking code
     const bool ragged = kDebug || (p.N % fa::kBlockN) != 0;
     auto go = [&](auto kern) { kern<<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg); };
-    if (pair) {
+    if (pingpong) {
+        auto gopp = [&](auto kern_fn) {
+            kern_fn<<<grid, dim3(fa::pp::kThreads), fa::pp::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
+        };
+        // (the debug build of this kernel exists for aligned shapes too: its cycle trace must time the code that ships)
+        const bool rag = (p.N % fa::kBlockN) != 0;
+        if (p.dtype == FA_DTYPE_BF16) {
+            if (rag) gopp(fa::pp::fa_fwd_kernel_pp<true, kDebug, true>);
+            else gopp(fa::pp::fa_fwd_kernel_pp<true, kDebug, false>);
+        } else {
+            if (rag) gopp(fa::pp::fa_fwd_kernel_pp<false, kDebug, true>);
+            else gopp(fa::pp::fa_fwd_kernel_pp<false, kDebug, false>);
+        }
+    } else if (pair) {
         if (p.dtype == FA_DTYPE_BF16) {
             if (ragged) go(fa::fa_fwd_kernel_pair<true, kDebug, true>);
             else go(fa::fa_fwd_kernel_pair<true, false, false>);
@@ -282,12 +307,12 @@ const char* fa_last_error_string(void) { return g_err; }
 int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int fa_set_kernel_mode(int mode) {
-    if (mode != FA_MODE_AUTO && mode != FA_MODE_SINGLE && mode != FA_MODE_PAIR) return -1;
+    if (mode < FA_MODE_AUTO || mode > FA_MODE_PINGPONG) return -1;
     return g_mode.exchange(mode, std::memory_order_relaxed);
 }
 
 int fa_set_thread_kernel_mode(int mode) {
-    if (mode != -1 && mode != FA_MODE_AUTO && mode != FA_MODE_SINGLE && mode != FA_MODE_PAIR) return -2;
+    if (mode < -1 || mode > FA_MODE_PINGPONG) return -2;
     const int prev = t_mode;
     t_mode = mode;
     return prev;

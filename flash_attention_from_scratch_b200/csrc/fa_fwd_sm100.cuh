@@ -105,15 +105,6 @@ static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register
 #define FA_SHARED_S 1         // single-CTA kernel: 1 = generation 6, 0 = generation 4b (see top of file)
 #endif
 constexpr bool kSharedSDefault = FA_SHARED_S != 0;
-#ifndef FA_P_SMEM
-#define FA_P_SMEM 0           // generation 11 candidate, CTA pairs only -- COMPILED BUT NOT YET RUN ON A GPU
-                              // (the round's GPU budget was spent; validate with tools/gpu_variant_check.sh):
-                              // P travels through shared memory (A operand of an SS MMA) instead of tensor
-                              // memory, which frees 128 TMEM columns for one S accumulator PER Q tile and
-                              // removes the serial chain through the shared accumulator.
-                              // Shared memory: K/V ring 6 x 16 KiB, P tiles 2 x 32 KiB behind it (the O
-                              // staging buffers alias them).  Tensor memory: [0,128) S_0  [128,256) S_1.
-#endif
 #ifndef FA_UNIFORM_WARP
 #define FA_UNIFORM_WARP 1
 #endif
@@ -185,23 +176,15 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                             const FwdParams& prm, const FwdDebug& dbg) {
     constexpr bool kSharedS = kPair || kSharedSDefault;
     constexpr bool kLdSplit = !kRagged && (FA_LD_SPLIT != 0);
-    constexpr bool kPSmem = kPair && (FA_P_SMEM != 0);
-    constexpr int kStages = kPSmem ? 6 : kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
+    constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
     constexpr uint32_t kArrivals = kPair ? 8u : 4u;  // softmax warps arriving on one barrier
     constexpr int kRowsPerTile = (kPair ? 2 : 1) * kQStages * kBlockM;
-    // kPSmem: P_s tiles ([2 key halves][128 rows][128 B], 128B swizzle, like Q) behind a 6-slot ring; they
-    // end where the O staging buffers end.  The epilogue of warpgroup s stages O in the first 16 KiB of
-    // P_s: the last PV_s has read it (pv_done is waited first) and the next tile's P_s is written by the
-    // same warpgroup only after its TMA stores have read the staging buffer.
-    constexpr int kSmemP = kSmemKV + 6 * (kTileBytes / 2);
-    static_assert(!kPSmem || kSmemP + kQStages * kTileBytes == kSmemStage + kQStages * kHalfBytes,
-                  "P tiles must fit between the 6-slot ring and the barriers");
-    constexpr int kSmemO = kPSmem ? kSmemP : kSmemStage;                   // O staging of Q tile 0 ...
-    constexpr int kSmemOStride = kPSmem ? kTileBytes : kHalfBytes;         // ... and the step to tile 1
+    constexpr int kSmemO = kSmemStage;        // O staging of Q tile 0 ...
+    constexpr int kSmemOStride = kHalfBytes;  // ... and the step to tile 1
     auto col_s = [](int s) -> uint32_t {  // tensor-memory column of the S accumulator of Q tile s
-        return kPSmem ? static_cast<uint32_t>(s) * 128u : tmem_col_s<kPair || kSharedSDefault>(s);
+        return tmem_col_s<kPair || kSharedSDefault>(s);
     };
 
     // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, which makes every
@@ -245,9 +228,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kMaxStages + s); };
     const uint32_t s_free = bar0 + 8u * (14 + 2 * kMaxStages);                   // generation 6/7
     auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kMaxStages + s); };  // generation 6/7
-    // S accumulator of Q tile s has been read out: one barrier for the shared accumulator, one per tile
-    // with kPSmem (tile 1 borrows o_full(1), which only generation 4b uses)
-    auto s_free_of = [&](int s) { return (kPSmem && s == 1) ? o_full(1) : s_free; };
     const uint32_t tmem_ptr_smem = smem_base + kSmemTmemPtr;
 
     auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait(bar, parity, tag); };
@@ -296,7 +276,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 mbar_init(pv_done(s), 1);
             }
             mbar_init(s_free, kArrivals);
-            if constexpr (kPSmem) mbar_init(o_full(1), kArrivals);  // = s_free_of(1), see above
             for (int i = 0; i < kStages; ++i) {
                 mbar_init(kv_full(i), 1);
                 mbar_init(kv_empty(i), 1);
@@ -319,7 +298,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     }
     tc_fence_before();
     if constexpr (kPair) cluster_sync();  // the peer's barriers exist before anything targets them
-    else __syncthreads();
+    __syncthreads();  // (pairs: orders the TMEM-address word for compute-sanitizer's racecheck, which does not
+                      // model barrier.cluster; one CTA barrier per launch)
     tc_fence_after();
     // All 512 TMEM columns are allocated by the only CTA on this SM, so the base address is 0.
     // Using the literal keeps every tcgen05 operand warp-uniform (no R2UR per MMA).
@@ -459,84 +439,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                 }
             }
-            if constexpr (kPSmem) {
-                // ------- generation 11 candidate: one S accumulator per Q tile, P through smem -------
-                // Issue order per work tile:  S_0(0) S_1(0) | S_0(j+1) PV_0(j) S_1(j+1) PV_1(j) | ...
-                // (FA_P_SMEM=2:                S_0(0) S_1(0) | S_0(j+1) S_1(j+1) PV_0(j) PV_1(j) | ...)
-                // S_s(j+1) only waits for warpgroup s to have read S_s(j) out (start of ITS block j), so
-                // it retires ~1000 clk before it is needed; nothing links the two Q tiles any more.
-                int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
-                uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of all per-tile barriers
-                int it = 0;
-                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
-                    auto issue_s2 = [&](int s, int jj) {  // S_s(jj) = Q_s K_jj^T into S_s
-                        const int itk = base + 2 * jj;
-                        const uint32_t gg = g0 + (uint32_t)jj;  // S_s accumulators produced before this one
-                        wait(kv_full(slot_of(itk)), parity_of(itk), 200);
-                        if (jj == 0) wait(q_full(s), (uint32_t)(it & 1), 210 + s);
-                        if (gg > 0) wait(s_free_of(s), (gg - 1u) & 1u, 270 + s);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_qk(s, slot_of(itk));
-                            commit(s_full(s));
-                            if (jj + 1 == n_blocks) commit(q_empty(s));  // last use of Q_s
-                            if (s == 1) commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
-                        }
-                        __syncwarp();
-                    };
-                    auto issue_pv_smem = [&](int s, uint64_t b0, bool accumulate, int k_begin, int k_end) {
-                        // A = P_s from shared memory (K-major: k-step = +32 B, second 64 keys at +16 KiB)
-                        const uint64_t a0 =
-                            umma_smem_desc_sw128(smem_base + kSmemP + s * kTileBytes, 16, 1024);
-#pragma unroll
-                        for (int k = k_begin; k < k_end; ++k) {
-                            const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
-                            const uint32_t a_off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
-                            umma_ss_2cta(tmem_base + tmem_col_o(s), a0 + a_off, b0 + ((k * 2048) >> 4),
-                                         idesc_pv, acc);
-                        }
-                    };
-                    auto issue_o2 = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
-                        const int itv = base + 2 * j + 1;
-                        const uint64_t vd = v_desc(slot_of(itv));
-                        const uint32_t par = (g0 + (uint32_t)j) & 1u;
-                        wait(kv_full(slot_of(itv)), parity_of(itv), 220);
-                        wait(p_full(s), par, 230 + s);  // first 96 keys of P_s(j) stored, O_s rescaled
-                        if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
-                            wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
-                        tc_fence_after();
-                        if (elect_one()) issue_pv_smem(s, vd, j > 0, 0, kSplitP ? 6 : 8);
-                        __syncwarp();
-                        if constexpr (kSplitP) {
-                            wait(p_last(s), par, 250 + s);  // last 32 keys of P_s(j)
-                            tc_fence_after();
-                        }
-                        if (elect_one()) {
-                            if constexpr (kSplitP) issue_pv_smem(s, vd, true, 6, 8);
-                            commit(pv_done(s));
-                            if (s == 1) commit(kv_empty(slot_of(itv)));
-                        }
-                        __syncwarp();
-                    };
-                    issue_s2(0, 0);
-                    issue_s2(1, 0);
-                    for (int j = 0; level >= 4 && j < n_blocks; ++j) {
-                        if constexpr (FA_P_SMEM == 2) {  // both S first: S_1(j+1) gets ~1100 clk of slack
-                            if (j + 1 < n_blocks) issue_s2(0, j + 1);
-                            if (j + 1 < n_blocks) issue_s2(1, j + 1);
-                            issue_o2(0, j);
-                            issue_o2(1, j);
-                        } else {
-                            if (j + 1 < n_blocks) issue_s2(0, j + 1);
-                            issue_o2(0, j);
-                            if (j + 1 < n_blocks) issue_s2(1, j + 1);
-                            issue_o2(1, j);
-                        }
-                    }
-                    base += 2 * n_blocks;
-                    g0 += (uint32_t)n_blocks;
-                }
-            } else if constexpr (kSharedS) {
+            if constexpr (kSharedS) {
                 // ------------- generation 6 / 7: one shared S accumulator -------------
                 // Issue order per work tile (n = n_blocks):
                 //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
@@ -816,9 +719,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         // above the reduction of the first half; a never-true dependency on m_lo
                         // keeps it behind
                         const uint32_t skew = (__float_as_uint(m_lo) == 0x7fc12345u) ? 8u : 0u;
-                        if (lane == 0) arrive_leader(s_free_of(s) + skew);
+                        if (lane == 0) arrive_leader(s_free + skew);
                     } else {
-                        if (lane == 0) arrive_leader(s_free_of(s));
+                        if (lane == 0) arrive_leader(s_free);
                     }
                 }
                 if constexpr (kDebug) {
@@ -908,22 +811,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                             }
                         }
                     }
-                    if constexpr (kPSmem) {
-                        // keys [32 q, 32 q + 32) of this row = 64 B = four 16-byte chunks of the
-                        // 128B-swizzled K-major tile the PV MMA reads as its A operand
-                        uint8_t* p_row = smem_gen + kSmemP + s * kTileBytes + (q >> 1) * kHalfBytes + row * 128;
-#pragma unroll
-                        for (int cidx = 0; cidx < 4; ++cidx) {
-                            const int chunk = ((q & 1) * 4 + cidx) ^ (row & 7);
-                            *reinterpret_cast<uint4*>(p_row + chunk * 16) =
-                                make_uint4(pk[4 * cidx], pk[4 * cidx + 1], pk[4 * cidx + 2], pk[4 * cidx + 3]);
-                        }
-                    } else {
-                        tmem_st_32x32b_x16(t_p + q * 16, pk);
-                    }
+                    tmem_st_32x32b_x16(t_p + q * 16, pk);
                     if (kSplitP && q == 2) {
-                        if constexpr (kPSmem) fence_proxy_async_smem();  // generic stores -> tensor-core reads
-                        else tmem_wait_st();
+                        tmem_wait_st();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) arrive_leader(p_full(s));
@@ -932,8 +822,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                     }
                 }
-                if constexpr (kPSmem) fence_proxy_async_smem();
-                else tmem_wait_st();
+                tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_leader(kSplitP ? p_last(s) : p_full(s));

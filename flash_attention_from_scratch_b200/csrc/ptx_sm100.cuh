@@ -14,6 +14,12 @@ namespace fa {
 #ifndef FA_HANG_GUARD
 #define FA_HANG_GUARD 0
 #endif
+#ifndef FA_WAIT_HINT
+#define FA_WAIT_HINT 0    // > 0: suspend-time hint (ns) passed to every mbarrier.try_wait (power experiment)
+#endif
+#ifndef FA_WAIT_SLEEP
+#define FA_WAIT_SLEEP 0   // > 0: nanosleep(ns) after every failed mbarrier.try_wait (power experiment)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -90,8 +96,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     __trap();
 #else
     (void)tag;
+#if FA_WAIT_HINT
+    // try_wait with an explicit suspend-time hint: the warp may sleep in hardware for up to that many ns
+    // per attempt instead of the (short) default limit
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"((uint32_t)FA_WAIT_HINT)
+            : "memory");
+    } while (!ok);
+#else
     while (!mbar_try_wait(bar, parity)) {
+#if FA_WAIT_SLEEP
+        __nanosleep(FA_WAIT_SLEEP);
+#endif
     }
+#endif
+#endif
+}
+
+// Waits for two barriers at once: both try_waits are in flight together, so two phases that completed long
+// ago cost one ~90-cycle round trip instead of two (it matters for the MMA-issuing warps, whose own
+// instruction time per KV block is what paces the tensor pipe).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b,
+                                           int tag = 0) {
+#if FA_HANG_GUARD
+    mbar_wait(bar_a, par_a, tag);
+    mbar_wait(bar_b, par_b, tag + 1);
+#else
+    (void)tag;
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+            "and.pred p, p, q;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+            : "memory");
+    } while (!ok);
 #endif
 }
 
@@ -261,6 +310,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same with release semantics at cluster scope (orders this thread's earlier generic-proxy writes for
+// an observer in the other CTA; ptxas emits a MEMBAR for it)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                  "r"(ncols)
@@ -322,6 +376,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
           "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
           "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }

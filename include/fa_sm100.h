@@ -93,6 +93,8 @@ int64_t fa_launch_count(void);
 #define FA_MODE_AUTO 0
 #define FA_MODE_SINGLE 1
 #define FA_MODE_PAIR 2
+#define FA_MODE_PINGPONG 3 /* CTA pairs, one 128-row Q tile per CTA, the two softmax warpgroups alternate KV
+                              blocks on two S accumulators (csrc/fa_fwd_pp_sm100.cuh); tile = 256 rows */
 int fa_set_kernel_mode(int mode);
 
 /* Same choice for the CALLING THREAD only; overrides the process-wide mode until reset with -1.

@@ -17,8 +17,6 @@ from flash_attention_from_scratch_b200 import build as fa_build  # noqa: E402
 VARIANTS = {
     # name: defines   (every library holds the single-CTA kernel and the CTA-pair kernel; FA_SM100_MODE picks)
     "base": {},
-    "psmem": {"FA_P_SMEM": 1},            # generation 11 candidate (pair): P through smem, S per Q tile -- untested
-    "psmem2": {"FA_P_SMEM": 2},           # same, both S of a block issued before the two PV -- untested
     "nouwarp": {"FA_UNIFORM_WARP": 0},    # warp index straight from threadIdx (generation 7 code shape)
     "emu6": {"FA_EMU_PAIRS": 6},
     "emu8": {"FA_EMU_PAIRS": 8},
@@ -30,6 +28,13 @@ VARIANTS = {
     "emu0": {"FA_EMU_PAIRS": 0},
     "emu6_6": {"FA_EMU_PAIRS": 6, "FA_EMU_PAIRS_LAST": 6},
     "nosplit": {"FA_SPLIT_P": 0},
+    "ppnotoken": {"FA_PP_TOKEN": 0},       # ping-pong kernel without the exp2-phase token
+    "ppnoskew": {"FA_PP_SKEW_NS": 0},
+    "ppnoprobe": {"FA_PP_PROBE": 0},
+    "ppexpv1": {"FA_EXP_VARIANT": 1},
+    "ppnotokprobe": {"FA_PP_TOKEN": 0, "FA_PP_PROBE": 1},
+    "hint": {"FA_WAIT_HINT": 10000000},   # CUTLASS-style 10 ms suspend-time hint on every try_wait
+    "sleep32": {"FA_WAIT_SLEEP": 32},     # nanosleep back-off in the wait loops
 }
 
 

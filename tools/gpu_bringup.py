@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--knobs", type=int, nargs=8, default=[16, 1024, 16384, 1024, 2048, 0, 8, 4])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bringup.json"))
     ap.add_argument("--quick", action="store_true", help="fewer shapes after the level ladder")
+    ap.add_argument("--levels", default="1,2,3,4", help="bring-up levels to run (the ping-pong kernel has 1 and 4)")
     args = ap.parse_args()
     if args.one:
         run_one(args)
@@ -177,7 +178,7 @@ def main():
     base = ["--dtype", "bf16", "--B", 1, "--N", 512, "--H", 1]
     default = [0, 0, 0, 0, 0, 0, 0]
     passed_level = 0
-    for level in (1, 2, 3, 4):
+    for level in [int(x) for x in args.levels.split(",")]:
         r = spawn(base + ["--knobs"] + default + [level], env=guard)
         rec(f"level{level}", r)
         good_here = r.get("rc") == 0 and (

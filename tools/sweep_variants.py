@@ -16,10 +16,12 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "sweep.json"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--timeout", type=int, default=120, help="per variant and mode; a timeout stops the sweep")
     ap.add_argument("--modes", default="auto", help="comma list of FA_SM100_MODE values (auto, single, pair)")
     args = ap.parse_args()
     vdir = ROOT / "flash_attention_from_scratch_b200" / "csrc" / "variants"
     rows = []
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
     for lib in sorted(vdir.glob("libfa_*.so")):
         name = lib.stem[len("libfa_"):]
         if name.startswith("guard_"):  # bring-up builds (tools/build_variants.py --guard), not for timing
@@ -28,9 +30,16 @@ def main():
             continue
         for mode in args.modes.split(","):
             env = dict(os.environ, FA_SM100_LIB=str(lib), FA_SM100_MODE=mode)
-            p = subprocess.run([sys.executable, str(ROOT / "tools" / "quick_bench.py"), "--shapes", args.shapes,
-                                "--reps", str(args.reps), "--check"], capture_output=True, text=True, env=env,
-                               timeout=300)
+            try:
+                p = subprocess.run([sys.executable, str(ROOT / "tools" / "quick_bench.py"), "--shapes", args.shapes,
+                                    "--reps", str(args.reps), "--check"], capture_output=True, text=True, env=env,
+                                   timeout=args.timeout)
+            except subprocess.TimeoutExpired:
+                print(name, mode, "TIMEOUT (hang?) -- stopping the sweep", flush=True)
+                rows.append({"variant": name, "mode": mode, "timeout": True})
+                with open(args.out, "w") as f:
+                    json.dump(rows, f, indent=1)
+                return 3
             for line in p.stdout.splitlines():
                 try:
                     r = json.loads(line)
@@ -49,4 +58,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())
