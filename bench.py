@@ -7,6 +7,7 @@ A "step" is ONE pass of the hot path (one launch of the fused attention forward)
 synthetic Q/K/V already resident in HBM.  Workloads (BASELINE.json `configs`):
 
   headline  bf16 (B=4, N=4096, H=32, d=128) per GPU            -- configs[1], the default
+  sweep     bf16 H=16, N in {512..16384} with the reference's batch sizes, harmonic mean -- configs[2]
   dtype16k  fp16|bf16 (8, 8192, 16, 128) per GPU               -- configs[3]  (--dtype fp16)
   shard16k  bf16 global (8, 16384, 32, 128) split over the ranks -- configs[4] (strong scaling)
 
@@ -16,7 +17,8 @@ barrier and the max-over-ranks of the device time.  Default scaling is WEAK: eac
 per-GPU headline problem (global batch = 4 N).
 
 Prints ONE JSON line (rank 0) with the contract keys plus `roofline`, `cpu_baseline`, `e2e`,
-`clocks`, `gpu_launches`.  `--impl reference` times the reference-side CPU implementation of the
+`clocks`, `gpu_launches` and `sustained` (the same launches back to back for >= 2 s: the power-capped regime,
+with >= 100 NVML samples of clock and power; `value` itself is the short-region figure the contract asks for).  `--impl reference` times the reference-side CPU implementation of the
 path (torch CPU attention = the reference's own test oracle family, see oracle/) instead.
 """
 from __future__ import annotations
@@ -34,9 +36,15 @@ sys.path.insert(0, ROOT)
 METRIC = "attention TFLOPs @ seq_len=4096 d_head=128; % of B200 bf16 tensor-core peak"
 UNIT = "TFLOP/s"
 
+# the reference's benchmark shapes: BATCH_SIZE_FOR_SEQ_LEN and BENCHMARK_N_HEADS = 16
+# (/root/reference/py/flash_helpers/test/utils.py:9-17)
+SWEEP_SHAPES = [(16, 512, 16, 128), (16, 1024, 16, 128), (16, 2048, 16, 128), (16, 4096, 16, 128),
+                (8, 8192, 16, 128), (4, 16384, 16, 128)]
+
 WORKLOADS = {
     # name: (B, N, H, d, default dtype, scaling)
     "headline": (4, 4096, 32, 128, "bf16", "weak"),
+    "sweep": (16, 4096, 16, 128, "bf16", "weak"),  # placeholder shape: see SWEEP_SHAPES
     "dtype16k": (8, 8192, 16, 128, "bf16", "weak"),
     "shard16k": (8, 16384, 32, 128, "bf16", "strong"),
 }
@@ -78,11 +86,12 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
-def kernel_name(seq_len):
-    """The kernel the C ABI launches for this sequence length (csrc/fa_api.cu: use_pair_kernel)."""
-    mode = os.environ.get("FA_SM100_MODE", "auto")
-    pair = mode == "pair" or (mode != "single" and seq_len > 1024)
-    return "fa::fa_fwd_kernel_pair (2-CTA clusters)" if pair else "fa::fa_fwd_kernel"
+def kernel_name():
+    """The kernel the library launched last on this thread (asked from the C ABI: fa_last_kernel)."""
+    from flash_attention_from_scratch_b200 import _lib
+
+    return {"fa_fwd_kernel": "fa::fa_fwd_kernel", "fa_fwd_kernel_pair": "fa::fa_fwd_kernel_pair (2-CTA clusters)",
+            "fa_fwd_kernel_pp": "fa::pp::fa_fwd_kernel_pp (2-CTA clusters, KV ping-pong)"}.get(_lib.last_kernel(), "?")
 
 
 def load_ncu_traffic():
@@ -98,9 +107,10 @@ def load_ncu_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples = []
         self.power_mw = []
         self.reasons = set()
@@ -139,7 +149,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def result(self):
         if not self.ok or not self.samples:
@@ -149,7 +159,35 @@ class ClockSampler(threading.Thread):
                "samples": len(s)}
         if self.power_mw:
             out["power_w_max"] = max(self.power_mw) / 1000.0
+            out["power_w_mean"] = sum(self.power_mw) / len(self.power_mw) / 1000.0
         return out
+
+
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index`, BEFORE any pinned host buffer is
+    allocated (first touch then places the pages on that NUMA node).  Returns a short description."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"cpus {cpus[0]}-{cpus[-1]} ({len(cpus)})"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
+def respawn_under_torchrun(n):
+    """`python bench.py --gpus N` without a launcher: start the N ranks ourselves, the way the driver does."""
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    os.execv(sys.executable, cmd)
 
 
 def cpu_attention_baseline(shape, dtype_name, reps, warmup=1):
@@ -216,14 +254,19 @@ def main():
     ap.add_argument("--dtype", default=None, choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = WORKLOADS[args.workload][4]
     args.warmup = max(args.warmup, 3)
 
+    if "WORLD_SIZE" not in os.environ and args.gpus > 1:
+        respawn_under_torchrun(args.gpus)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and args.impl != "reference":
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but the launcher started WORLD_SIZE={world} ranks")
     if args.impl == "reference":
         run_reference(args, rank, world)
         return 0
@@ -243,62 +286,133 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned buffer exists (e2e leg)
     B, N, H, D, _, scaling = WORKLOADS[args.workload]
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    if scaling == "weak":
-        gB, gH = B * world, H
-        lB, lH = B, H
-    else:
-        sh = shard_for_rank(B, H, world, rank)
-        gB, gH = B, H
-        lB, lH = sh.batch, sh.heads
-    shape = (lB, N, lH, D)
-    local_flops = matmul_flops(*shape)
-    global_flops = matmul_flops(gB, N, gH, D)
-
-    # two rotating input sets (each set Q+K+V+O = 4 tensors; the headline set is 512 MiB >> 126 MB
-    # L2), so no step starts with its inputs cached by the previous one
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    sets = []
-    for _ in range(2):
-        q, k, v = (torch.randn(shape, device=dev, dtype=dt, generator=gen) for _ in range(3))
-        sets.append((q, k, v, torch.empty_like(q)))
     stream = torch.cuda.current_stream()
-
-    def step(i):
-        q, k, v, o = sets[i & 1]
-        fa.forward(None, q, k, v, o)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    n0 = _lib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step(i)
-        ev[i + 1].record(stream)
-    barrier()
-    launches = _lib.launch_count() - n0
-    sampler.stop_flag.set()
-    sampler.join()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    kern_ms = sum(per_launch_ms) / len(per_launch_ms)
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = t.item()
-    ms_per_step = total_ms_max / args.steps
-    value = global_flops / (ms_per_step * 1e-3) / 1e12
+    def local_shape(B, N, H, D):
+        if scaling == "weak":
+            return (B, N, H, D), (B * world, N, H, D)
+        sh = shard_for_rank(B, H, world, rank)
+        return (sh.batch, N, sh.heads, D), (B, N, H, D)
+
+    def make_sets(shape):
+        """Rotating input sets, >= 512 MiB in total (L2 is 126 MB), so no step starts with its inputs cached by
+        an earlier one.  The headline set (Q, K, V, O) is 512 MiB by itself: two sets."""
+        set_bytes = 4 * shape[0] * shape[1] * shape[2] * shape[3] * 2
+        n_sets = max(2, -(-(512 << 20) // set_bytes))
+        gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+        sets = []
+        for _ in range(n_sets):
+            q, k, v = (torch.randn(shape, device=dev, dtype=dt, generator=gen) for _ in range(3))
+            sets.append((q, k, v, torch.empty_like(q)))
+        return sets
+
+    def measure(sets, steps, warmup):
+        """W warm-ups, then exactly `steps` launches bracketed by barrier + synchronize; device time from
+        cudaEvents on the launch stream, max over ranks.  Returns (ms/step, mean kernel ms, launches, clocks)."""
+        def step(i):
+            q, k, v, o = sets[i % len(sets)]
+            fa.forward(None, q, k, v, o)
+
+        for i in range(warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n0 = _lib.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        ev[0].record(stream)
+        for i in range(steps):
+            step(i)
+            ev[i + 1].record(stream)
+        barrier()
+        launches = _lib.launch_count() - n0
+        sampler.stop_flag.set()
+        sampler.join()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, sum(per_launch) / len(per_launch), int(launches), sampler.result()
+
+    def measure_sustained(sets, flops_per_launch, seconds=2.2, chunk=25):
+        """The same launches back to back for >= `seconds`: the power-capped regime a long-running caller sees.
+        NVML clock / power every 10 ms (>= 100 samples)."""
+        def step(i):
+            q, k, v, o = sets[i % len(sets)]
+            fa.forward(None, q, k, v, o)
+
+        barrier()
+        sampler = ClockSampler(local_rank, period=0.01)
+        sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(chunk):
+                step(n)
+                n += 1
+            if n % (4 * chunk) == 0:
+                torch.cuda.current_stream().synchronize()  # keep the launch queue bounded, never empty for long
+        e1.record(stream)
+        barrier()
+        sampler.stop_flag.set()
+        sampler.join()
+        ms = e0.elapsed_time(e1)
+        clk = sampler.result()
+        return {"value": flops_per_launch * n / (ms * 1e-3) / 1e12, "unit": UNIT, "launches": n,
+                "region_s": ms * 1e-3, "sm_mhz_median": clk.get("sm_mhz"), "power_w_mean": clk.get("power_w_mean"),
+                "power_w_max": clk.get("power_w_max"), "nvml_samples": clk.get("samples"),
+                "reasons": clk.get("reasons")}
+
+    sweep_rows = None
+    if args.workload == "sweep":
+        # BASELINE config 3: one figure per sequence length, value = harmonic mean over the six
+        sweep_rows = []
+        launches = 0
+        clocks = None
+        for (sB, sN, sH, sD) in SWEEP_SHAPES:
+            shape, gshape = local_shape(sB, sN, sH, sD)
+            sets = make_sets(shape)
+            ms_step, k_ms, n_l, clk = measure(sets, args.steps, args.warmup)
+            launches += n_l
+            clocks = clk if sN == 4096 else clocks
+            sweep_rows.append({"seq_len": sN, "batch": gshape[0], "n_heads": sH, "ms_per_step": ms_step,
+                               "tflops": matmul_flops(*gshape) / (ms_step * 1e-3) / 1e12,
+                               "kernel_tflops": matmul_flops(*shape) / (k_ms * 1e-3) / 1e12, "kernel": kernel_name(),
+                               "sm_mhz": clk.get("sm_mhz"), "reasons": clk.get("reasons")})
+            del sets
+            torch.cuda.empty_cache()
+        value = len(sweep_rows) / sum(1.0 / r["tflops"] for r in sweep_rows)
+        ms_per_step = sum(r["ms_per_step"] for r in sweep_rows)  # one pass over the six shapes
+        B, N, H, D = SWEEP_SHAPES[3]
+    shape, gshape = local_shape(B, N, H, D)
+    lB, lH = shape[0], shape[2]
+    gB, gH = gshape[0], gshape[2]
+    local_flops = matmul_flops(*shape)
+    global_flops = matmul_flops(*gshape)
+    sets = make_sets(shape)
+    if sweep_rows is None:
+        ms_per_step, kern_ms, launches, clocks = measure(sets, args.steps, args.warmup)
+        value = global_flops / (ms_per_step * 1e-3) / 1e12
+    else:
+        kern_ms = local_flops / (sweep_rows[3]["kernel_tflops"] * 1e12) * 1e3
+    sustained_rec = None
+    if not args.no_sustained:
+        sustained_rec = measure_sustained(sets, global_flops)
+        if world > 1:
+            sustained_rec["note"] = "rank 0's clock; flops of all ranks over rank 0's device time"
 
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI
     e2e = None
@@ -323,6 +437,7 @@ def main():
         e2e = {"value": global_flops / te.item() / 1e12, "unit": UNIT,
                "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "ms_per_step": te.item() * 1e3, "steps": e2e_steps,
+               "host_numa_binding": numa,
                "path": "fa_fwd_host (C ABI): pinned host Q,K,V -> HBM, kernel, O -> pinned host; "
                        "batch-pipelined copies inside the timed region"}
 
@@ -341,29 +456,44 @@ def main():
     if rank == 0:
         burst, sustained, how = load_peaks()
         achieved = local_flops / (kern_ms * 1e-3) / 1e12
+        region_ms = ms_per_step * args.steps
+        wl = (f"{args.workload}: {args.dtype} fused attention forward, per-GPU (B,N,H,d)=({lB},{N},{lH},{D}), "
+              f"global ({gB},{N},{gH},{D}), non-causal, randn inputs")
+        if sweep_rows is not None:
+            wl = (f"sweep: {args.dtype} fused attention forward, H=16, d=128, (batch, seq_len) = "
+                  "(16,512) (16,1024) (16,2048) (16,4096) (8,8192) (4,16384) per GPU "
+                  "[the reference's benchmark shapes]; value = harmonic mean of the six TFLOP/s; roofline = the "
+                  "seq_len 4096 point")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {args.dtype} fused attention forward, per-GPU (B,N,H,d)="
-                            f"({lB},{N},{lH},{D}), global ({gB},{N},{gH},{D}), non-causal, randn inputs",
+                "workload": wl,
                 "flops_per_step": global_flops, "flop_model": "4*B*H*N^2*d",
-                "l2_policy": "inputs larger than L2: two rotating 4-tensor sets (>= 512 MiB each at the "
-                             "headline) so no step re-reads a cached input",
+                "l2_policy": "inputs larger than L2: rotating 4-tensor sets, >= 512 MiB in total (two at the "
+                             "headline), so no step re-reads a cached input",
                 "parallelism": f"dp{world} over (batch x heads), no collective on the data path",
                 "timing": "cudaEvents on the launch stream, barrier+synchronize both sides, max over ranks",
+                "regime": f"burst: {args.steps} back-to-back launches, timed region {region_ms:.1f} ms (the "
+                          "board is power-capped under this kernel; see `sustained` for the >= 2 s figure)",
             },
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": UNIT,
                          "frac": achieved / burst, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, "
-                         f"cuBLAS burst; sustained {sustained})", "frac_of_sustained": achieved / sustained,
-                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": kernel_name(N),
+                         f"cuBLAS burst; sustained {sustained})",
+                         "frac_of_nominal_2250": achieved / 2250.0, "kernel": kernel_name(),
                          "kernel_ms": kern_ms, "traffic": load_ncu_traffic()},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "clocks": sampler.result(),
+            "clocks": clocks,
         }
+        if sustained_rec is not None:
+            sustained_rec["peak_sustained"] = sustained
+            sustained_rec["frac_of_cublas_sustained"] = sustained_rec["value"] / sustained
+            line["sustained"] = sustained_rec
+        if sweep_rows is not None:
+            line["sweep"] = sweep_rows
         emit(line)
     if world > 1:
         dist.barrier()

@@ -29,6 +29,8 @@ SYMBOLS = {
     "fa_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
     "fa_launch_count": (_L, []),
+    "fa_last_kernel": (_I, []),
+    "fa_tensor_map_cache_stats": (_I, [C.POINTER(_L), C.POINTER(_L)]),
     "fa_set_kernel_mode": (_I, [_I]),
     "fa_set_thread_kernel_mode": (_I, [_I]),
     "fa_fwd_debug": (_I, _FWD_ARGS + [_P, C.POINTER(C.c_uint32), _P]),
@@ -67,7 +69,19 @@ def launch_count() -> int:
     return int(load().fa_launch_count())
 
 
-MODE_AUTO, MODE_SINGLE, MODE_PAIR = 0, 1, 2
+MODE_AUTO, MODE_SINGLE, MODE_PAIR, MODE_PINGPONG = 0, 1, 2, 3
+KERNEL_NAMES = {MODE_SINGLE: "fa_fwd_kernel", MODE_PAIR: "fa_fwd_kernel_pair", MODE_PINGPONG: "fa_fwd_kernel_pp"}
+
+
+def last_kernel() -> str:
+    """Name of the kernel the calling thread's last launch used (what AUTO picked)."""
+    return KERNEL_NAMES.get(int(load().fa_last_kernel()), "none")
+
+
+def tensor_map_cache_stats() -> dict:
+    h, m = C.c_int64(), C.c_int64()
+    load().fa_tensor_map_cache_stats(C.byref(h), C.byref(m))
+    return {"hits": h.value, "misses": m.value}
 
 
 def set_kernel_mode(mode: int) -> int:
@@ -87,14 +101,15 @@ class thread_kernel_mode:
         self.prev = -1
 
     def __enter__(self):
-        if self.mode in (MODE_SINGLE, MODE_PAIR):
+        if self.mode in (MODE_SINGLE, MODE_PAIR, MODE_PINGPONG):
             self.prev = int(load().fa_set_thread_kernel_mode(self.mode))
         elif self.mode != 0:
-            raise ValueError(f"invalid cta_group {self.mode} (0 = auto, 1 = single CTAs, 2 = CTA pairs)")
+            raise ValueError(f"invalid cta_group {self.mode} (0 = auto, 1 = single CTAs, 2 = CTA pairs, "
+                             "3 = CTA pairs, ping-pong kernel)")
         return self
 
     def __exit__(self, *exc):
-        if self.mode in (MODE_SINGLE, MODE_PAIR):
+        if self.mode in (MODE_SINGLE, MODE_PAIR, MODE_PINGPONG):
             load().fa_set_thread_kernel_mode(self.prev)
         return False
 

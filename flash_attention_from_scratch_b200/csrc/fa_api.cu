@@ -85,10 +85,16 @@ cudaError_t set_smem_attr() {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fa::pp::kSmemLaunchBytes);
 }
 
-// Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  Measured with generation 9 on the
-// reference's benchmark shapes (profiles/r01_g9_mode_threshold.txt): single CTAs win up to seq_len 512
-// (+4 %; +21 % at 256), the mappings tie at 1024, CTA pairs win from 2048 on (+1.4 %).
-constexpr int kPairMinSeqLen = 1024;  // AUTO: CTA pairs for seq_len > this
+// Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  Measured on one B200 with the reference's benchmark
+// shapes (profiles/r02_sweep_g14.json, TFLOP/s, mean of 12, L2 flushed):
+//   seq_len      512   1024   2048   4096(H=32)   8192   16384
+//   ping-pong    846   1278   1442      1464       1474    1374
+//   CTA pairs    711   1198   1431      1483       1512    1460
+//   single CTAs  738   1210   1399      1441       1439    1357
+// The ping-pong kernel has twice as many (half as large) work tiles and no serial chain through a shared S
+// accumulator, which wins while tiles are short; the pair kernel moves half the K/V bytes per FLOP and runs its
+// epilogue half as often, which wins from 4096 on.
+constexpr int kPingPongMaxSeqLen = 2048;  // AUTO: ping-pong kernel up to this, CTA pairs above
 std::atomic<int> g_mode{[] {
     const char* m = getenv("FA_SM100_MODE");
     if (m != nullptr && strcmp(m, "single") == 0) return FA_MODE_SINGLE;
@@ -97,10 +103,13 @@ std::atomic<int> g_mode{[] {
     return FA_MODE_AUTO;
 }()};
 thread_local int t_mode = -1;  // fa_set_thread_kernel_mode: per-thread override, -1 = none
-int pick_kernel(int seq_len) {  // FA_MODE_SINGLE, FA_MODE_PAIR or FA_MODE_PINGPONG
+int pick_kernel(int seq_len, int batch, int n_heads, int n_sms) {  // FA_MODE_SINGLE, _PAIR or _PINGPONG
     const int mode = t_mode >= 0 ? t_mode : g_mode.load(std::memory_order_relaxed);
     if (mode != FA_MODE_AUTO) return mode;
-    return seq_len > kPairMinSeqLen ? FA_MODE_PAIR : FA_MODE_SINGLE;
+    (void)batch;
+    (void)n_heads;
+    (void)n_sms;
+    return seq_len > kPingPongMaxSeqLen ? FA_MODE_PAIR : FA_MODE_PINGPONG;
 }
 
 // One-time per-device setup: capability check + opt-in dynamic shared memory
@@ -208,74 +217,141 @@ int validate(const Problem& p, int d_head) {
     return FA_OK;
 }
 
-template <bool kDebug>
-int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
+// Per-thread cache of encoded tensor maps, keyed by everything cuTensorMapEncodeTiled reads (pointer, shape,
+// strides, dtype, box height).  A map depends on nothing else, so a hit is valid even if the allocation was
+// freed and handed out again.  Four encodes cost ~3-5 us of host time per call, which is visible next to the
+// 45 us kernel of the (16, 512, 16, 128) benchmark shape (SURVEY.md 8(b) suggested the cache).
+struct MapKey {
+    const void* ptr;
+    int B, N, H, dtype, box_rows;
+    int64_t sb, sn, sh;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && B == o.B && N == o.N && H == o.H && dtype == o.dtype && box_rows == o.box_rows &&
+               sb == o.sb && sn == o.sn && sh == o.sh;
+    }
+};
+struct MapSlot {
+    bool valid = false;
+    MapKey key{};
+    CUtensorMap map;
+};
+constexpr int kMapCacheSlots = 32;
+thread_local MapSlot t_map_cache[kMapCacheSlots];
+std::atomic<int64_t> g_map_hits{0}, g_map_misses{0};
+
+int cached_tensor_map(CUtensorMap* out, const void* ptr, const Problem& p, int box_rows) {
+    const MapKey key{ptr, p.B, p.N, p.H, p.dtype, box_rows, p.sb, p.sn, p.sh};
+    const uint64_t h = (reinterpret_cast<uintptr_t>(ptr) >> 8) * 0x9E3779B97F4A7C15ull + (uint64_t)box_rows * 31 +
+                       (uint64_t)p.N * 131 + (uint64_t)p.H * 7 + (uint64_t)p.B;
+    MapSlot& slot = t_map_cache[(h >> 32) % kMapCacheSlots];
+    if (slot.valid && slot.key == key) {
+        *out = slot.map;
+        g_map_hits.fetch_add(1, std::memory_order_relaxed);
+        return FA_OK;
+    }
+    int rc = make_tensor_map(out, ptr, p, box_rows);
+    if (rc != FA_OK) return rc;
+    slot.valid = true;
+    slot.key = key;
+    slot.map = *out;
+    g_map_misses.fetch_add(1, std::memory_order_relaxed);
+    return FA_OK;
+}
+
+// Everything a launch needs that can be computed before the stream is touched (so that fa_fwd_timed's event
+// bracket holds the kernel only).
+struct LaunchPlan {
+    int kern = FA_MODE_SINGLE;
+    CUtensorMap tq, tk, tv, to;
+    fa::FwdParams prm;
+    dim3 grid, block;
+    int smem = 0;
+    bool ragged = false;
+};
+thread_local int t_last_kernel = -1;  // FA_MODE_* of the calling thread's last launch (fa_last_kernel)
+
+int prepare(const Problem& p, bool debug, LaunchPlan* plan) {
     int dev = -1;
     FA_CUDA(cudaGetDevice(&dev));
     int rc = init_device(dev);
     if (rc != FA_OK) return rc;
-
-    const int kern = pick_kernel(p.N);
+    const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
+    const int kern = pick_kernel(p.N, p.B, p.H, n_sms);
     const bool pingpong = kern == FA_MODE_PINGPONG;
     const bool pair = kern != FA_MODE_SINGLE;  // clusters of two CTAs
     const int rows_per_tile = pingpong ? 2 * fa::kBlockM : (pair ? 2 : 1) * fa::kQStages * fa::kBlockM;
-    CUtensorMap tq, tk, tv, to;
-    if ((rc = make_tensor_map(&tq, p.q, p)) != FA_OK) return rc;
+    plan->kern = kern;
+    if ((rc = cached_tensor_map(&plan->tq, p.q, p, 128)) != FA_OK) return rc;
     // a CTA of a pair loads 64 keys of every K block
-    if ((rc = make_tensor_map(&tk, p.k, p, pair ? 64 : 128)) != FA_OK) return rc;
-    if ((rc = make_tensor_map(&tv, p.v, p)) != FA_OK) return rc;
-    if ((rc = make_tensor_map(&to, p.o, p)) != FA_OK) return rc;
+    if ((rc = cached_tensor_map(&plan->tk, p.k, p, pair ? 64 : 128)) != FA_OK) return rc;
+    if ((rc = cached_tensor_map(&plan->tv, p.v, p, 128)) != FA_OK) return rc;
+    if ((rc = cached_tensor_map(&plan->to, p.o, p, 128)) != FA_OK) return rc;
 
-    fa::FwdParams prm;
+    fa::FwdParams& prm = plan->prm;
     prm.batch = p.B;
     prm.seq_len = p.N;
     prm.n_heads = p.H;
     prm.n_kv_blocks = (p.N + fa::kBlockN - 1) / fa::kBlockN;
     prm.n_q_groups = (p.N + rows_per_tile - 1) / rows_per_tile;
     prm.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt((double)fa::kHeadDim));
-
     const long long n_tiles = 1LL * p.B * p.H * prm.n_q_groups;
     if (n_tiles > 0x7fffffffLL) return fail(FA_ERR_ARG, "problem too large: %lld tiles", n_tiles);
     prm.n_tiles = static_cast<int>(n_tiles);
     // persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int n_sms = g_dev[dev].n_sms > 0 ? g_dev[dev].n_sms : 148;
     const long long n_workers = pair ? n_sms / 2 : n_sms;  // CTAs, or CTA pairs (one cluster per TPC)
     const unsigned n_active = (unsigned)(n_tiles < n_workers ? n_tiles : n_workers);
-    dim3 grid(pair ? 2 * n_active : n_active), block(fa::kNumThreads);
-    // one instantiation per (dtype, ragged tail?); the debug build always carries the masking code
-    const bool ragged = kDebug || (p.N % fa::kBlockN) != 0;
-    auto go = [&](auto kern) { kern<<<grid, block, fa::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg); };
-    if (pingpong) {
-        auto gopp = [&](auto kern_fn) {
-            kern_fn<<<grid, dim3(fa::pp::kThreads), fa::pp::kSmemLaunchBytes, stream>>>(tq, tk, tv, to, prm, dbg);
-        };
-        // (the debug build of this kernel exists for aligned shapes too: its cycle trace must time the code that ships)
-        const bool rag = (p.N % fa::kBlockN) != 0;
-        if (p.dtype == FA_DTYPE_BF16) {
-            if (rag) gopp(fa::pp::fa_fwd_kernel_pp<true, kDebug, true>);
-            else gopp(fa::pp::fa_fwd_kernel_pp<true, kDebug, false>);
+    plan->grid = dim3(pair ? 2 * n_active : n_active);
+    plan->block = dim3(pingpong ? fa::pp::kThreads : fa::kNumThreads);
+    plan->smem = pingpong ? fa::pp::kSmemLaunchBytes : fa::kSmemLaunchBytes;
+    // one instantiation per (dtype, ragged tail?); the debug build of the generation-9 kernels always carries the
+    // masking code, the ping-pong kernel's debug build exists for aligned shapes too (its cycle trace must time
+    // the code that ships)
+    const bool rag = (p.N % fa::kBlockN) != 0;
+    plan->ragged = pingpong ? rag : (debug || rag);
+    return FA_OK;
+}
+
+template <bool kDebug>
+int issue(const Problem& p, const LaunchPlan& L, cudaStream_t stream, const fa::FwdDebug& dbg) {
+    auto go = [&](auto kern) {
+        kern<<<L.grid, L.block, L.smem, stream>>>(L.tq, L.tk, L.tv, L.to, L.prm, dbg);
+    };
+    const bool bf16 = p.dtype == FA_DTYPE_BF16;
+    if (L.kern == FA_MODE_PINGPONG) {
+        if (bf16) {
+            if (L.ragged) go(fa::pp::fa_fwd_kernel_pp<true, kDebug, true>);
+            else go(fa::pp::fa_fwd_kernel_pp<true, kDebug, false>);
         } else {
-            if (rag) gopp(fa::pp::fa_fwd_kernel_pp<false, kDebug, true>);
-            else gopp(fa::pp::fa_fwd_kernel_pp<false, kDebug, false>);
+            if (L.ragged) go(fa::pp::fa_fwd_kernel_pp<false, kDebug, true>);
+            else go(fa::pp::fa_fwd_kernel_pp<false, kDebug, false>);
         }
-    } else if (pair) {
-        if (p.dtype == FA_DTYPE_BF16) {
-            if (ragged) go(fa::fa_fwd_kernel_pair<true, kDebug, true>);
+    } else if (L.kern == FA_MODE_PAIR) {
+        if (bf16) {
+            if (L.ragged) go(fa::fa_fwd_kernel_pair<true, kDebug, true>);
             else go(fa::fa_fwd_kernel_pair<true, false, false>);
         } else {
-            if (ragged) go(fa::fa_fwd_kernel_pair<false, kDebug, true>);
+            if (L.ragged) go(fa::fa_fwd_kernel_pair<false, kDebug, true>);
             else go(fa::fa_fwd_kernel_pair<false, false, false>);
         }
-    } else if (p.dtype == FA_DTYPE_BF16) {
-        if (ragged) go(fa::fa_fwd_kernel<true, kDebug, true>);
+    } else if (bf16) {
+        if (L.ragged) go(fa::fa_fwd_kernel<true, kDebug, true>);
         else go(fa::fa_fwd_kernel<true, false, false>);
     } else {
-        if (ragged) go(fa::fa_fwd_kernel<false, kDebug, true>);
+        if (L.ragged) go(fa::fa_fwd_kernel<false, kDebug, true>);
         else go(fa::fa_fwd_kernel<false, false, false>);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    t_last_kernel = L.kern;
     FA_CUDA(cudaGetLastError());
     return FA_OK;
+}
+
+template <bool kDebug>
+int launch(const Problem& p, cudaStream_t stream, const fa::FwdDebug& dbg) {
+    LaunchPlan plan;
+    int rc = prepare(p, kDebug, &plan);
+    if (rc != FA_OK) return rc;
+    return issue<kDebug>(p, plan, stream, dbg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,6 +381,14 @@ extern "C" {
 const char* fa_last_error_string(void) { return g_err; }
 
 int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fa_last_kernel(void) { return t_last_kernel; }
+
+int fa_tensor_map_cache_stats(int64_t* hits, int64_t* misses) {
+    if (hits) *hits = g_map_hits.load(std::memory_order_relaxed);
+    if (misses) *misses = g_map_misses.load(std::memory_order_relaxed);
+    return FA_OK;
+}
 
 int fa_set_kernel_mode(int mode) {
     if (mode < FA_MODE_AUTO || mode > FA_MODE_PINGPONG) return -1;
@@ -355,17 +439,28 @@ int fa_fwd_timed(const void* q, const void* k, const void* v, void* o, int batch
     int rc = validate(p, d_head);
     if (rc != FA_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaEvent_t e0, e1;
+    // device checks, kernel choice and tensor maps first: the event bracket holds the kernel only
+    LaunchPlan plan;
+    rc = prepare(p, false, &plan);
+    if (rc != FA_OK) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     FA_CUDA(cudaEventCreate(&e0));
-    FA_CUDA(cudaEventCreate(&e1));
+    cudaError_t e = cudaEventCreate(&e1);
+    if (e != cudaSuccess) {
+        cudaEventDestroy(e0);
+        return fail(FA_ERR_LAUNCH, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
     fa::FwdDebug dbg{};
-    cudaEventRecord(e0, st);
-    rc = launch<false>(p, st, dbg);
-    cudaEventRecord(e1, st);
-    cudaError_t e = cudaEventSynchronize(e1);
+    e = cudaEventRecord(e0, st);
+    if (e == cudaSuccess) {
+        rc = issue<false>(p, plan, st, dbg);
+        e = cudaEventRecord(e1, st);
+    }
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     if (rc == FA_OK && e != cudaSuccess)
         rc = fail(FA_ERR_LAUNCH, "kernel execution failed: %s", cudaGetErrorString(e));
-    if (rc == FA_OK) cudaEventElapsedTime(ms, e0, e1);
+    if (rc == FA_OK && cudaEventElapsedTime(ms, e0, e1) != cudaSuccess)
+        rc = fail(FA_ERR_LAUNCH, "cudaEventElapsedTime failed");
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
@@ -424,8 +519,26 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
                     d_head);
     if (batch <= 0 || seq_len <= 0 || n_heads <= 0)
         return fail(FA_ERR_ARG, "batch, seq_len and n_heads must be positive");
-    FA_CUDA(cudaSetDevice(device));
+    // the caller's current device is restored on every path
+    struct DeviceGuard {
+        int prev = -1;
+        explicit DeviceGuard(int d) {
+            cudaGetDevice(&prev);
+            if (prev != d) cudaSetDevice(d);
+            else prev = -1;
+        }
+        ~DeviceGuard() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } guard(device);
+    {
+        int cur = -1;
+        FA_CUDA(cudaGetDevice(&cur));
+        if (cur != device) return fail(FA_ERR_DEVICE, "cudaSetDevice(%d) failed", device);
+    }
     HostWorkspace& w = g_ws[device];
+    // the workspace and its three streams are per device: calls for one device are serialised, calls for
+    // different devices (one per rank / thread) run concurrently
     std::lock_guard<std::mutex> lk(w.mu);
     const size_t per_batch = (size_t)seq_len * n_heads * d_head * 2;
     const size_t total = per_batch * batch;
@@ -442,32 +555,50 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
     while ((int)w.ev_in.size() < batch) {
         cudaEvent_t a, b;
         FA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        FA_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        if (cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventDestroy(a);
+            return fail(FA_ERR_LAUNCH, "cudaEventCreate failed");
+        }
         w.ev_in.push_back(a);
         w.ev_run.push_back(b);
     }
     const int64_t sh = d_head, sn = (int64_t)n_heads * d_head, sb = (int64_t)seq_len * sn;
-    // Software pipeline over the batch dimension: H2D(b+1) overlaps kernel(b) overlaps D2H(b-1).
-    for (int b = 0; b < batch; ++b) {
+    // Software pipeline over the batch dimension: H2D(b+1) overlaps kernel(b) overlaps D2H(b-1).  On an error
+    // nothing may stay in flight against the caller's host buffers: the three streams are drained before
+    // returning.
+    int rc = FA_OK;
+    auto step = [&](cudaError_t e, const char* what) {
+        if (rc == FA_OK && e != cudaSuccess) rc = fail(FA_ERR_LAUNCH, "%s failed: %s", what, cudaGetErrorString(e));
+        return rc == FA_OK;
+    };
+    for (int b = 0; b < batch && rc == FA_OK; ++b) {
         const size_t off = per_batch * b;
         const void* src[3] = {q_host, k_host, v_host};
-        for (int t = 0; t < 3; ++t)
-            FA_CUDA(cudaMemcpyAsync((char*)w.d[t] + off, (const char*)src[t] + off, per_batch,
-                                    cudaMemcpyHostToDevice, w.s_in));
-        FA_CUDA(cudaEventRecord(w.ev_in[b], w.s_in));
-        FA_CUDA(cudaStreamWaitEvent(w.s_run, w.ev_in[b], 0));
-        int rc = fa_fwd((char*)w.d[0] + off, (char*)w.d[1] + off, (char*)w.d[2] + off,
-                        (char*)w.d[3] + off, 1, seq_len, n_heads, d_head, sb, sn, sh, dtype,
-                        w.s_run);
-        if (rc != FA_OK) return rc;
-        FA_CUDA(cudaEventRecord(w.ev_run[b], w.s_run));
-        FA_CUDA(cudaStreamWaitEvent(w.s_out, w.ev_run[b], 0));
-        FA_CUDA(cudaMemcpyAsync((char*)o_host + off, (char*)w.d[3] + off, per_batch,
-                                cudaMemcpyDeviceToHost, w.s_out));
+        for (int t = 0; t < 3 && rc == FA_OK; ++t)
+            step(cudaMemcpyAsync((char*)w.d[t] + off, (const char*)src[t] + off, per_batch, cudaMemcpyHostToDevice,
+                                 w.s_in), "cudaMemcpyAsync (H2D)");
+        if (!step(cudaEventRecord(w.ev_in[b], w.s_in), "cudaEventRecord")) break;
+        if (!step(cudaStreamWaitEvent(w.s_run, w.ev_in[b], 0), "cudaStreamWaitEvent")) break;
+        const int frc = fa_fwd((char*)w.d[0] + off, (char*)w.d[1] + off, (char*)w.d[2] + off, (char*)w.d[3] + off, 1,
+                               seq_len, n_heads, d_head, sb, sn, sh, dtype, w.s_run);
+        if (frc != FA_OK) {
+            rc = frc;  // fa_fwd has set the error text
+            break;
+        }
+        if (!step(cudaEventRecord(w.ev_run[b], w.s_run), "cudaEventRecord")) break;
+        if (!step(cudaStreamWaitEvent(w.s_out, w.ev_run[b], 0), "cudaStreamWaitEvent")) break;
+        step(cudaMemcpyAsync((char*)o_host + off, (char*)w.d[3] + off, per_batch, cudaMemcpyDeviceToHost, w.s_out),
+             "cudaMemcpyAsync (D2H)");
     }
-    FA_CUDA(cudaStreamSynchronize(w.s_out));
-    FA_CUDA(cudaStreamSynchronize(w.s_run));
-    return FA_OK;
+    const cudaError_t d0 = cudaStreamSynchronize(w.s_in);
+    const cudaError_t d1 = cudaStreamSynchronize(w.s_run);
+    const cudaError_t d2 = cudaStreamSynchronize(w.s_out);
+    if (rc == FA_OK) {
+        step(d0, "cudaStreamSynchronize");
+        step(d1, "cudaStreamSynchronize");
+        step(d2, "cudaStreamSynchronize");
+    }
+    return rc;
 }
 
 }  // extern "C"

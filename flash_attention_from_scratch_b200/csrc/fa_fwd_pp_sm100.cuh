@@ -20,9 +20,9 @@
 // 80 B/clk of shared-memory operand reads.
 //
 // Shared row state.  Both warpgroups scale P against the same reference maximum m (the one O is
-// accumulated against).  It lives in shared memory (one float per row) and is handed from the owner of
-// block G-1 to the owner of block G through a per-warp-pair mbarrier (`m_ready`): the owner of G reads it
-// after its own row max is known, decides whether the lazy rescale is due (max grew by more than 2^8,
+// accumulated against).  It lives in shared memory (one word per row, stamped with a 4-bit block sequence
+// number, polled with plain loads: no barrier, no fence) and is handed from the owner of block G-1 to the
+// owner of block G: the owner of G reads it after its own row max is known, decides whether the lazy rescale is due (max grew by more than 2^8,
 // same rule as generation 9), rescales O if so (after PV(G-1) retired), publishes the new m and only then
 // spends ~1500 clk on the exponentials -- so the hand-over is ~1500 clk ahead of the consumer.  Each
 // warpgroup keeps a partial row sum l_w relative to the m it last saw and re-bases it when m moved; at the
@@ -56,7 +56,7 @@ constexpr int kSmemStage = kSmemV + kVStages * kSlotBytes;    // O staging: two 
 constexpr int kSmemM = kSmemStage + 2 * kHalfBytes;           // float m[128]: reference max of O, per row
 constexpr int kSmemL = kSmemM + 128 * 4;                      // float2 lm[2][128]: (partial row sum, its reference max)
 constexpr int kSmemBar = kSmemL + 2 * 128 * 8;                //   of either softmax warpgroup, for the epilogue
-constexpr int kNumBarriers = 4 + 2 * kStages + 11 + 8 + 8 + 3;
+constexpr int kNumBarriers = 4 + 2 * kStages + 11 + 8 + 3 + 8;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
 constexpr int kSmemLaunchBytes = kSmemTotal;  // the base is 1024-byte aligned by declaration (checked at run time)
@@ -71,6 +71,11 @@ constexpr int kThreads = 512;  // warps 0-3 / 4-7 softmax, 8 MMA, 9 TMA, 10-11 i
 #define FA_PP_REGS_CTRL 56
 #endif
 static_assert(256 * FA_PP_REGS_SOFTMAX + 128 * FA_PP_REGS_EPI + 128 * FA_PP_REGS_CTRL <= 65536, "register pool");
+#ifndef FA_PP_MSLOT
+#define FA_PP_MSLOT 0     // how the reference max travels between the warpgroups: 1 = one sequence-stamped word per
+                          // row polled with plain loads, 0 = per-warp-pair mbarrier + plain word (racecheck-clean)
+#endif
+constexpr bool kMSlot = FA_PP_MSLOT != 0;
 #ifndef FA_PP_PROBE
 #define FA_PP_PROBE 1     // test the barriers a softmax warp needs later in a block early (see the softmax loop)
 #endif
@@ -83,7 +88,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;  // S_w at kColS + 128 w, P_w at kColP + 64 w
 
 #ifndef FA_PP_TOKEN
-#define FA_PP_TOKEN 1     // 1: the exp2 phases of the two warps that share an SM sub-partition (warp q of either
+#define FA_PP_TOKEN 0     // 1: the exp2 phases of the two warps that share an SM sub-partition (warp q of either
                           // warpgroup) strictly alternate in block order, so each runs with the MUFU to itself
                           // (16 ex2/clk/SM: ~840 clk per block when alone, twice that when both are in it) and
                           // P(G) completions -- hence PV / S issue -- are spaced evenly instead of in bursts
@@ -125,10 +130,10 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
     auto p_last = [&](int w) { return bar0 + 8u * (kB + 6 + w); };            // leader, 8 warps
     const uint32_t o_free = bar0 + 8u * (kB + 8);                             // leader, 8 warps (epilogue)
     auto pv_done = [&](int w) { return bar0 + 8u * (kB + 9 + w); };           // both
-    auto m_ready = [&](int w, int q) { return bar0 + 8u * (kB + 11 + 4 * w + q); };  // local, 1 warp
-    auto exp_done = [&](int w, int q) { return bar0 + 8u * (kB + 19 + 4 * w + q); };  // local, 1 warp
-    auto lm_ready = [&](int w) { return bar0 + 8u * (kB + 27 + w); };         // local, 4 warps
-    const uint32_t lm_free = bar0 + 8u * (kB + 29);                           // local, 4 warps (epilogue)
+    auto exp_done = [&](int w, int q) { return bar0 + 8u * (kB + 11 + 4 * w + q); };  // local, 1 warp
+    auto lm_ready = [&](int w) { return bar0 + 8u * (kB + 19 + w); };         // local, 4 warps
+    const uint32_t lm_free = bar0 + 8u * (kB + 21);                           // local, 4 warps (epilogue)
+    auto m_ready = [&](int w, int q) { return bar0 + 8u * (kB + 22 + 4 * w + q); };  // local, 1 warp (!kMSlot)
     static_assert(kB + 30 == kNumBarriers, "barrier count");
 
     auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait(bar, parity, tag); };
@@ -166,8 +171,8 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 mbar_init(p_full(b), 8);
                 mbar_init(p_last(b), 8);
                 mbar_init(pv_done(b), 1);
-                for (int q = 0; q < 4; ++q) mbar_init(m_ready(b, q), 1);
                 for (int q = 0; q < 4; ++q) mbar_init(exp_done(b, q), 1);
+                for (int q = 0; q < 4; ++q) mbar_init(m_ready(b, q), 1);
             }
             mbar_init(o_free, 8);
             mbar_init(lm_ready(0), 4);
@@ -186,6 +191,9 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
         __syncwarp();
         tmem_alloc_2cta(smem_base + kSmemTmemPtr, kTmemCols);
         tmem_relinquish_2cta();
+    } else if (warp < 4) {
+        // row-state slots start with sequence number 0 (see the softmax loop)
+        reinterpret_cast<uint32_t*>(smem_gen + kSmemM)[threadIdx.x] = 0u;
     } else if (warp == 9 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
@@ -389,7 +397,7 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
         const uint32_t t_o = tmem_base + lane_sel + kColO;
         const float c = prm.scale_log2;
         const int kv_tail = prm.seq_len & (kBlockN - 1);
-        float* sm_m = reinterpret_cast<float*>(smem_gen + kSmemM);
+        const uint32_t slot_m = smem_base + kSmemM + 4u * row;  // this row's shared state word
         float2* sm_lm = reinterpret_cast<float2*>(smem_gen + kSmemL);
         if (FA_PP_SKEW_NS > 0 && w == 1) __nanosleep(FA_PP_SKEW_NS);
 
@@ -419,20 +427,17 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 // warpgroup's own time per block is what paces the kernel.  The barriers needed later in the block
                 // (m of block g-1 published, PV(g-2) retired) are tested here, under the tensor-memory load, and
                 // only waited for at the point of use if the probe failed.
-                const uint32_t par_m = (uint32_t)(((g - 1) >> 1) & 1);
-                bool m_probed = false, p_probed = false;
+                bool p_probed = false;
                 float m_prev = 0.f;
+                uint32_t slot_early = ((uint32_t)g & 15u) ^ 1u;  // "not yet": forces a load at the point of use
                 if constexpr (!kRagged) {
                     tmem_ld_32x32b_x32(t_s, sr[0]);
                     tmem_ld_32x32b_x32(t_s + 32, sr[1]);
-                    if constexpr (kProbe) {
-                        if (j > 0) m_probed = mbar_try_wait(m_ready(w ^ 1, wq), par_m);
-                        p_probed = mbar_try_wait(pv_done(w), par ^ 1u);
-                        if (m_probed) m_prev = sm_m[row];
-                    }
+                    if constexpr (kProbe) p_probed = mbar_test_wait(pv_done(w), par ^ 1u);
                     tmem_wait_ld();
                     tmem_ld_32x32b_x32(t_s + 64, sr[2]);
                     tmem_ld_32x32b_x32(t_s + 96, sr[3]);
+                    if constexpr (kMSlot) slot_early = lds_volatile_u32(slot_m);  // row state of block g-1, normally there
                     m_lo = row_max_frags<0, 2>(sr);
                     tmem_wait_ld();
                 } else {
@@ -469,15 +474,37 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 }
 
                 // ---- shared row state: the reference max of O ----
+                // Decision of block g-1 (other warpgroup, same row) published: its slot carries the block's sequence number
+                // in the four low mantissa bits of m.  Also awaited by the first block of a tile, which does not use the
+                // value: the slot has one writer at a time, in block order.
+                uint32_t slot_v = slot_early;
+                if constexpr (kMSlot) {
+#if FA_HANG_GUARD
+                    for (uint32_t spin = 0; (slot_v & 15u) != ((uint32_t)g & 15u); ++spin) {
+                        if (spin > (1u << 22)) {
+                            diag_record(0xDEAD0000u | 340u, (uint32_t)g, threadIdx.x, blockIdx.x);
+                            __trap();
+                        }
+                        slot_v = lds_volatile_u32(slot_m);
+                    }
+#else
+                    while ((slot_v & 15u) != ((uint32_t)g & 15u)) {
+                        __nanosleep(32);
+                        slot_v = lds_volatile_u32(slot_m);
+                    }
+#endif
+                } else {
+                    if (g > 0) wait(m_ready(w ^ 1, wq), (uint32_t)(((g - 1) >> 1) & 1), 340 + w);
+                    slot_v = lds_volatile_u32(slot_m);
+                }
+                m_prev = __uint_as_float(slot_v & ~15u);
+                // the candidate for the new reference max is already in its published (truncated) form, so that
+                // alpha, P and l are all computed against exactly the value the other warpgroup will read
+                mx = __uint_as_float(__float_as_uint(mx) & ~15u);
                 float m_cur;
                 if (j == 0) {
                     m_cur = mx;  // first block of the tile: O is overwritten by PV(g) (accumulate = 0)
                 } else {
-                    // decision of block g-1 (other warpgroup) published
-                    if (!m_probed) {
-                        wait(m_ready(w ^ 1, wq), par_m, 340 + w);
-                        m_prev = sm_m[row];
-                    }
                     if (have_l) l_run *= ex2_approx((m_known - m_prev) * c);  // exactly 1 when m did not move
                     const float delta = (mx - m_prev) * c;
                     const bool need = delta > kRescaleThreshold;
@@ -503,11 +530,16 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                         l_run *= alpha;
                     }
                 }
-                sm_m[row] = m_cur;
+                // Publish: one 32-bit word per row = m with its four low mantissa bits replaced by the sequence number
+                // of the NEXT block (a single word needs no fence and no barrier; m only has to be the same value
+                // for everybody who scales against it, so the owner uses the truncated value too).
+                sts_volatile_u32(slot_m, __float_as_uint(m_cur) | ((uint32_t)(g + 1) & 15u));
+                if constexpr (!kMSlot) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(m_ready(w, wq));
+                }
                 m_known = m_cur;
                 have_l = true;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(m_ready(w, wq));  // release: the next block's owner may decide
                 if constexpr (kDebug) {
                     if (tr) tr[3] = clk32();
                 }
@@ -555,7 +587,7 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                     }
                 }
                 if constexpr (kProbe) {  // S of this warpgroup's next block (normally there since ~1000 clk)
-                    s_probed = mbar_try_wait(s_full(w), par ^ 1u);
+                    s_probed = mbar_test_wait(s_full(w), par ^ 1u);
                 }
                 tmem_wait_st();
                 tc_fence_before();

@@ -105,6 +105,14 @@ static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register
 #define FA_SHARED_S 1         // single-CTA kernel: 1 = generation 6, 0 = generation 4b (see top of file)
 #endif
 constexpr bool kSharedSDefault = FA_SHARED_S != 0;
+#ifndef FA_DUAL_ISSUE
+#define FA_DUAL_ISSUE 1       // generation 14 (shared-S protocols): TWO MMA-issuing warps -- warp 8 streams the QK^T
+                              // groups, warp 10 the PV groups -- and separate K and V rings.  A cycle trace of the
+                              // ping-pong kernel (profiles/r02_pp_notes.md) showed that ONE in-order issuing warp
+                              // needs ~1400 clk of its own instruction time per KV block (mbarrier waits at ~90 clk
+                              // even when long complete, ~25-30 clk per tcgen05.mma, commits): in this kernel that
+                              // time sits inside the serial chain through the shared S accumulator.
+#endif
 #ifndef FA_UNIFORM_WARP
 #define FA_UNIFORM_WARP 1
 #endif
@@ -176,6 +184,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                             const FwdParams& prm, const FwdDebug& dbg) {
     constexpr bool kSharedS = kPair || kSharedSDefault;
     constexpr bool kLdSplit = !kRagged && (FA_LD_SPLIT != 0);
+    constexpr bool kDual = kSharedS && (FA_DUAL_ISSUE != 0);
     constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
@@ -340,10 +349,13 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     __syncwarp();
                 };
                 auto load_kv = [&](bool is_k, int blk) {
-                    const int slot = item % kStages;
-                    const uint32_t use = item / kStages;
+                    // kDual: K blocks cycle through the first half of the slots, V blocks through the second
+                    // (item = 2 * block + is_v, running across tiles); else one ring in consumption order
+                    constexpr int kH = kStages / 2;
+                    const int slot = kDual ? (is_k ? 0 : kH) + (item >> 1) % kH : item % kStages;
+                    const uint32_t use = kDual ? (uint32_t)((item >> 1) / kH) : (uint32_t)(item / kStages);
                     wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
-                    if (kDebug && level >= 7 && item >= kStages) {
+                    if (kDebug && level >= 7 && use > 0) {
                         // ablation: keep the barrier protocol, skip the copy (the slot keeps old data)
                         if (is_leader && elect_one()) mbar_arrive(kv_full(slot));
                     } else if (elect_one()) {
@@ -439,7 +451,37 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                 }
             }
-            if constexpr (kSharedS) {
+            if constexpr (kDual) {
+                // ------------- generation 14: this warp streams the QK^T groups only -------------
+                //   S_0(0) S_1(0) S_0(1) S_1(1) ...   each into the shared accumulator as soon as the previous S was
+                //   read out (`s_free`) and K_j landed; the PV groups are issued by warp 10.
+                constexpr int kH = kStages / 2;
+                int kb = 0;      // K blocks consumed so far (all tiles): ring slot / parity
+                uint32_t u = 0;  // S accumulators issued so far (all tiles): s_free parity
+                int it = 0;
+                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
+                    const int nb = (level >= 4) ? n_blocks : 1;
+                    for (int jj = 0; jj < nb; ++jj, ++kb) {
+                        const int slot = kb % kH;
+                        const uint64_t kd = k_desc(slot);
+                        wait(kv_full(slot), (uint32_t)((kb / kH) & 1), 200);
+#pragma unroll
+                        for (int s = 0; s < kQStages; ++s) {
+                            if (jj == 0) wait(q_full(s), (uint32_t)(it & 1), 210 + s);
+                            if (u > 0) wait(s_free, (u - 1u) & 1u, 270 + s);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_qk_b(s, kd);
+                                commit(s_full(s));
+                                if (jj + 1 == n_blocks) commit(q_empty(s));  // last use of Q_s
+                                if (s == 1) commit(kv_empty(slot));          // both tiles used K_jj
+                            }
+                            __syncwarp();
+                            ++u;
+                        }
+                    }
+                }
+            } else if constexpr (kSharedS) {
                 // ------------- generation 6 / 7: one shared S accumulator -------------
                 // Issue order per work tile (n = n_blocks):
                 //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
@@ -623,6 +665,56 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         item += has_next ? 2 : 1;
                     }
                 }
+            }
+        } else if (kDual && warp == 10 && is_leader) {
+            // ======================= MMA issuer 2 (generation 14): the PV groups =======================
+            //   PV_0(0) PV_1(0) PV_0(1) PV_1(1) ...   each as soon as P_s(j) is stored (96 + 32 keys) and V_j landed
+            constexpr int kM = kPair ? 2 * kBlockM : kBlockM;
+            constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kM, kHeadDim, true);
+            constexpr int kH = kStages / 2;
+            int vb = 0;       // V blocks consumed so far (all tiles)
+            uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of the p / pv barriers
+            int it = 0;
+            for (int tile = cta_lin; level >= 4 && tile < tile_end; tile += n_cta, ++it) {
+                for (int j = 0; j < n_blocks; ++j, ++vb) {
+                    const int slot = kH + vb % kH;
+                    const uint64_t vd =
+                        umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, kHalfBytes, 1024);
+                    const uint32_t par = (g0 + (uint32_t)j) & 1u;
+                    wait(kv_full(slot), (uint32_t)((vb / kH) & 1), 220);
+#pragma unroll
+                    for (int s = 0; s < kQStages; ++s) {
+                        wait(p_full(s), par, 230 + s);  // P_s(j) stored (first 96 keys), O_s rescaled
+                        if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
+                            wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
+                        tc_fence_after();
+                        auto pv = [&](int k_begin, int k_end) {
+#pragma unroll
+                            for (int k = k_begin; k < k_end; ++k) {
+                                const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+                                if constexpr (kPair)
+                                    umma_ts_2cta(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                                 vd + ((k * 2048) >> 4), idesc_pv, acc);
+                                else
+                                    umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                            vd + ((k * 2048) >> 4), idesc_pv, acc);
+                            }
+                        };
+                        if (elect_one()) pv(0, kSplitP ? 6 : 8);
+                        __syncwarp();
+                        if constexpr (kSplitP) {
+                            wait(p_last(s), par, 250 + s);  // last 32 keys of P_s(j)
+                            tc_fence_after();
+                        }
+                        if (elect_one()) {
+                            if constexpr (kSplitP) pv(6, 8);
+                            commit(pv_done(s));
+                            if (s == 1) commit(kv_empty(slot));
+                        }
+                        __syncwarp();
+                    }
+                }
+                g0 += (uint32_t)n_blocks;
             }
         } else if (warp == 10) {
             // ====================== tensor-pipe observer (cycle trace only) ======================

@@ -67,6 +67,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking test (try_wait may suspend the thread for a while when the phase is still running; this never does).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 // Blocks until the phase with the given parity has completed.  With FA_HANG_GUARD the spin is
 // bounded and traps with a diagnostic instead of hanging the GPU (bring-up builds only).
 #if FA_HANG_GUARD

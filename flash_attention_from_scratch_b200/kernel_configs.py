@@ -86,7 +86,8 @@ class FlashForwardKernelConfig:
     mma_double_buffer_loads: bool = False
     optimized_softmax: bool = True
     # Blackwell knob (not in the reference): machine mapping of the sm_100a kernel.  0 = the library's
-    # choice by sequence length, 1 = single CTAs (tcgen05 cta_group::1), 2 = 2-CTA clusters (cta_group::2).
+    # choice by sequence length, 1 = single CTAs (tcgen05 cta_group::1), 2 = 2-CTA clusters (cta_group::2),
+    # 3 = 2-CTA clusters running the KV ping-pong kernel (one Q tile per CTA, csrc/fa_fwd_pp_sm100.cuh).
     cta_group: int = 0
 
     def __str__(self) -> str:
@@ -110,7 +111,7 @@ class FlashForwardKernelConfig:
         return head + "+".join(feats)
 
     def kernel_name(self) -> str:
-        return "fa_fwd_kernel_pair" if self.cta_group == 2 else "fa_fwd_kernel"
+        return {2: "fa_fwd_kernel_pair", 3: "fa_fwd_kernel_pp"}.get(self.cta_group, "fa_fwd_kernel")
 
     def attn_flop(self, n_samples: int, n_heads: int, seq_len: int) -> int:
         return calc_self_attn_flop(n_samples, n_heads, seq_len, self.d_head)
@@ -138,7 +139,40 @@ def parse_kernel_name_into_config(text: str) -> FlashForwardKernelConfig:
         swizzled="swizzled" in feats, Q_mma_load_K_tiles=qt, K_mma_load_K_tiles=kt,
         V_mma_load_K_tiles=vt, mma_double_buffer_loads="buffer" in feats,
         optimized_softmax="opt_softmax" in feats,
-        cta_group=next((int(f[3:]) for f in feats if f in ("cta1", "cta2")), 0))
+        cta_group=next((int(f[3:]) for f in feats if f in ("cta1", "cta2", "cta3")), 0))
+
+
+_DEMANGLED_RE = re.compile(r"fa::(?:pp::)?(fa_fwd_kernel(?:_pair|_pp)?)<\(bool\)([01]), \(bool\)([01]), \(bool\)([01])>")
+
+
+def parse_flash_forward_kernel_config(kernel_name: str) -> FlashForwardKernelConfig:
+    """Kernel name as ncu prints it -> config.  The reference's ncu_bench.py imports this name
+    (/root/reference/tools/benchmark/ncu_bench.py:15,104; its own library only has
+    `parse_kernel_name_into_config`, kernel_configs.py:323-335, which is why that script is stale).  Accepts
+    the demangled sm_100a kernels (`void fa::fa_fwd_kernel_pair<(bool)1, (bool)0, (bool)0>(...)`: bf16?, debug?,
+    ragged?) and the short form."""
+    m = _DEMANGLED_RE.search(kernel_name)
+    if m:
+        kern, bf16, _debug, _ragged = m.groups()
+        return FlashForwardKernelConfig(dtype=DType.BF16 if bf16 == "1" else DType.FP16,
+                                        cta_group={"fa_fwd_kernel": 1, "fa_fwd_kernel_pair": 2, "fa_fwd_kernel_pp": 3}[kern])
+    return parse_kernel_name_into_config(kernel_name)
+
+
+def tile_softmax_flop(B_r: int, B_c: int, d_head: int) -> int:
+    return B_r * (4 * B_c + d_head + 4)  # kernel_configs.py:61-63 (kernels 6-16)
+
+
+def kv_tile_flop(B_r: int, B_c: int, d_head: int) -> int:
+    return 2 * B_r * d_head * B_c + 2 * B_r * B_c * d_head + tile_softmax_flop(B_r, B_c, d_head)
+
+
+def calc_total_flop(n_samples: int, n_heads: int, seq_len: int, B_r: int, B_c: int, d_head: int) -> int:
+    """The reference's tile-level FLOP model including the softmax arithmetic (kernel_configs.py:87-99),
+    used by its ncu_bench.py for the "total" column."""
+    assert seq_len % B_r == 0 and seq_len % B_c == 0
+    t_r, t_c = seq_len // B_r, seq_len // B_c
+    return t_r * (t_c * kv_tile_flop(B_r, B_c, d_head) + B_r * d_head) * n_samples * n_heads
 
 
 def get_kernels_to_build():
@@ -151,7 +185,7 @@ def get_autotuning_kernel_configs(dtypes=(DType.BF16, DType.FP16)):
     """The tuning grid of the sm_100a kernel: both machine mappings per dtype (the reference's grid of
     Ampere tile knobs, kernel_configs.py:364-455, has no meaning here).  Build-time knobs (exp2 emulation
     fraction, K/V ring depth, register split) are swept with tools/build_variants.py instead."""
-    return [FlashForwardKernelConfig(dtype=dt, cta_group=cg) for dt in dtypes for cg in (1, 2)]
+    return [FlashForwardKernelConfig(dtype=dt, cta_group=cg) for dt in dtypes for cg in (1, 2, 3)]
 
 
 def get_kernel_configs(kernels_key: str = ""):

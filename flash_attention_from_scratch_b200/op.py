@@ -125,6 +125,11 @@ def forward_host(q, k, v, o=None, device: int = 0):
         raise RuntimeError("Query, key and value tensors have same shape")
     if o is None:
         o = torch.empty_like(q, pin_memory=q.is_pinned())
+    elif o.is_cuda or not o.is_contiguous() or o.shape != q.shape or o.dtype != q.dtype:
+        # the library copies batch*seq*heads*128 elements into o: anything else would be written out of bounds
+        raise RuntimeError("o must be a contiguous host tensor with the shape and dtype of q")
+    if q.size(3) != 128:
+        raise RuntimeError("Kernel configuration was not found in flash_kernels.cuh")
     B, N, H, D = q.shape
     rc = lib.fa_fwd_host(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, N, H, D,
                          _DTYPE_CODE[q.dtype], device)

@@ -84,12 +84,13 @@ int64_t fa_launch_count(void);
 
 /* Which kernel a launch uses.  The reference selects one of its 85 template instantiations with the
  * kernel_cfg map lookup (flash_attention.cu:59-62); this library has two machine mappings of the same
- * arithmetic and picks by shape:
- *   FA_MODE_AUTO   (default): CTA pairs when seq_len > 1024, single CTAs otherwise (measured crossover)
- *   FA_MODE_SINGLE one CTA per SM, work tile = 256 query rows
- *   FA_MODE_PAIR   clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
+ * arithmetic (three kernels) and picks by shape:
+ *   FA_MODE_AUTO     (default): the ping-pong kernel up to seq_len 2048, CTA pairs above (measured crossover)
+ *   FA_MODE_SINGLE   one CTA per SM, work tile = 256 query rows
+ *   FA_MODE_PAIR     clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
+ *   FA_MODE_PINGPONG clusters of two CTAs, one 128-row Q tile per CTA, two S accumulators (tile = 256 rows)
  * Process-wide; returns the previous mode (or -1 for an invalid argument).  The environment variable
- * FA_SM100_MODE=auto|single|pair sets the initial value. */
+ * FA_SM100_MODE=auto|single|pair|pingpong sets the initial value. */
 #define FA_MODE_AUTO 0
 #define FA_MODE_SINGLE 1
 #define FA_MODE_PAIR 2
@@ -102,6 +103,14 @@ int fa_set_kernel_mode(int mode);
  * flash_attention.cu:59-62): the Python operator brackets a launch with it when kernel_cfg.cta_group is
  * 1 (single CTAs) or 2 (CTA pairs).  Returns the previous override (-1 = none), -2 for a bad argument. */
 int fa_set_thread_kernel_mode(int mode);
+
+/* FA_MODE_SINGLE / FA_MODE_PAIR / FA_MODE_PINGPONG of the calling thread's last launch (-1: none yet): what
+ * AUTO actually picked, so that callers (bench.py) need not re-implement the rule. */
+int fa_last_kernel(void);
+
+/* Hit / miss counters of the per-thread cache of encoded TMA tensor maps (key: pointer, shape, strides, dtype;
+ * the reference builds nothing per call, its kernel takes raw pointers: flash_attention.cu:107-110). */
+int fa_tensor_map_cache_stats(int64_t* hits, int64_t* misses);
 
 /* Bring-up entry: runs the debug instantiation with explicit descriptor knobs and a dump buffer
  * (see FwdDebug in csrc/fa_fwd_sm100.cuh).  knobs[7] = bring-up level (1 setup only, 2 TMA,

@@ -103,14 +103,33 @@ def test_kernel_configs_surface():
     for c in cfgs:
         assert parse_kernel_name_into_config(str(c)) == c
     assert get_kernel_configs("128,128") == cfgs and get_kernel_configs("64,64") == []
-    # the Blackwell tuning grid (KERNELS=tune): both machine mappings per dtype, round-tripping names
+    # the Blackwell tuning grid (KERNELS=tune): the three machine mappings per dtype, round-tripping names
     tune = get_kernel_configs("tune")
     assert sorted((c.dtype, c.cta_group) for c in tune) == sorted(
-        (dt, cg) for dt in (DType.FP16, DType.BF16) for cg in (1, 2))
+        (dt, cg) for dt in (DType.FP16, DType.BF16) for cg in (1, 2, 3))
     for c in tune:
         assert f"cta{c.cta_group}" in str(c) and parse_kernel_name_into_config(str(c)) == c
-    assert tune[0].kernel_name() in ("fa_fwd_kernel", "fa_fwd_kernel_pair")
+    assert tune[0].kernel_name() in ("fa_fwd_kernel", "fa_fwd_kernel_pair", "fa_fwd_kernel_pp")
+    assert {c.kernel_name() for c in tune} == {"fa_fwd_kernel", "fa_fwd_kernel_pair", "fa_fwd_kernel_pp"}
     assert all(c.cta_group == 0 and "cta" not in str(c) for c in cfgs)
     # FLOP model of the reference README (kernel_configs.py:102-103)
     assert calc_self_attn_flop(4, 32, 4096, 128) == 4 * 32 * (4 * 4096**2 * 128 + 6 * 4096**2)
     assert FlashForwardKernelConfig(dtype=DType.BF16).total_flop(4, 32, 4096) == 4 * 4 * 32 * 4096**2 * 128
+
+
+def test_forward_host_rejects_a_bad_output_buffer():
+    """fa_fwd_host copies batch*seq*heads*128 elements into `o`; anything but a contiguous host tensor of
+    q's shape and dtype would be written out of bounds, so the operator refuses it before the library is called."""
+    import torch
+
+    from flash_attention_from_scratch_b200 import op
+
+    q = torch.zeros(1, 128, 2, 128, dtype=torch.bfloat16)
+    for bad in (torch.zeros(1, 64, 2, 128, dtype=torch.bfloat16),              # too small
+                torch.zeros(1, 128, 2, 128, dtype=torch.float16),              # wrong dtype
+                torch.zeros(1, 128, 4, 128, dtype=torch.bfloat16)[:, :, ::2],  # not contiguous
+                ):
+        with pytest.raises(RuntimeError, match="contiguous host tensor"):
+            op.forward_host(q, q, q, bad)
+    with pytest.raises(RuntimeError, match="was not found"):
+        op.forward_host(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())

@@ -75,7 +75,7 @@ def simulate(n, tiles, k_stages=4, v_stages=4, verbose=False):
                 g = g0 + j
                 yield ("s_full%d" % w, (g >> 1) + 1)
                 sig("s_free%d" % w)
-                if j > 0:
+                if g > 0:  # the row-state slot has one writer at a time, in block order
                     yield ("m_ready%d" % (w ^ 1), ((g - 1) >> 1) + 1)
                 sig("m_ready%d" % w)
                 if g > 0:
