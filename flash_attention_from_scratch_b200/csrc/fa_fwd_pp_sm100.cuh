@@ -20,9 +20,9 @@
 // 80 B/clk of shared-memory operand reads.
 //
 // Shared row state.  Both warpgroups scale P against the same reference maximum m (the one O is
-// accumulated against).  It lives in shared memory (one word per row, stamped with a 4-bit block sequence
-// number, polled with plain loads: no barrier, no fence) and is handed from the owner of block G-1 to the
-// owner of block G: the owner of G reads it after its own row max is known, decides whether the lazy rescale is due (max grew by more than 2^8,
+// accumulated against).  It lives in shared memory (one word per row) and is handed from the owner of block
+// G-1 to the owner of block G -- sibling warps on the same SM sub-partition -- behind a 64-thread named
+// barrier: the owner of G reads it after its own row max is known, decides whether the lazy rescale is due (max grew by more than 2^8,
 // same rule as generation 9), rescales O if so (after PV(G-1) retired), publishes the new m and only then
 // spends ~1500 clk on the exponentials -- so the hand-over is ~1500 clk ahead of the consumer.  Each
 // warpgroup keeps a partial row sum l_w relative to the m it last saw and re-bases it when m moved; at the
@@ -56,7 +56,7 @@ constexpr int kSmemStage = kSmemV + kVStages * kSlotBytes;    // O staging: two 
 constexpr int kSmemM = kSmemStage + 2 * kHalfBytes;           // float m[128]: reference max of O, per row
 constexpr int kSmemL = kSmemM + 128 * 4;                      // float2 lm[2][128]: (partial row sum, its reference max)
 constexpr int kSmemBar = kSmemL + 2 * 128 * 8;                //   of either softmax warpgroup, for the epilogue
-constexpr int kNumBarriers = 4 + 2 * kStages + 11 + 8 + 3 + 8;
+constexpr int kNumBarriers = 4 + 2 * kStages + 11 + 8;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
 constexpr int kSmemLaunchBytes = kSmemTotal;  // the base is 1024-byte aligned by declaration (checked at run time)
@@ -71,11 +71,6 @@ constexpr int kThreads = 512;  // warps 0-3 / 4-7 softmax, 8 MMA, 9 TMA, 10-11 i
 #define FA_PP_REGS_CTRL 56
 #endif
 static_assert(256 * FA_PP_REGS_SOFTMAX + 128 * FA_PP_REGS_EPI + 128 * FA_PP_REGS_CTRL <= 65536, "register pool");
-#ifndef FA_PP_MSLOT
-#define FA_PP_MSLOT 0     // how the reference max travels between the warpgroups: 1 = one sequence-stamped word per
-                          // row polled with plain loads, 0 = per-warp-pair mbarrier + plain word (racecheck-clean)
-#endif
-constexpr bool kMSlot = FA_PP_MSLOT != 0;
 #ifndef FA_PP_PROBE
 #define FA_PP_PROBE 1     // test the barriers a softmax warp needs later in a block early (see the softmax loop)
 #endif
@@ -131,10 +126,14 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
     const uint32_t o_free = bar0 + 8u * (kB + 8);                             // leader, 8 warps (epilogue)
     auto pv_done = [&](int w) { return bar0 + 8u * (kB + 9 + w); };           // both
     auto exp_done = [&](int w, int q) { return bar0 + 8u * (kB + 11 + 4 * w + q); };  // local, 1 warp
-    auto lm_ready = [&](int w) { return bar0 + 8u * (kB + 19 + w); };         // local, 4 warps
-    const uint32_t lm_free = bar0 + 8u * (kB + 21);                           // local, 4 warps (epilogue)
-    auto m_ready = [&](int w, int q) { return bar0 + 8u * (kB + 22 + 4 * w + q); };  // local, 1 warp (!kMSlot)
-    static_assert(kB + 30 == kNumBarriers, "barrier count");
+    // Hand-overs through generic shared memory use NAMED barriers (bar.arrive by the writer, bar.sync by the reader:
+    // cheap, and compute-sanitizer's racecheck understands them, which it does not for mbarrier-ordered accesses):
+    //   2 + 4 w + q   reference max of a block published by warp q of warpgroup w        (64 threads)
+    //   10 + w        (l, m) of a tile handed from softmax warpgroup w to the epilogue   (256 threads)
+    //   12 + w        ... and read by the epilogue: warpgroup w may overwrite its pair    (256 threads)
+    //   1             epilogue warpgroup: staging buffer written / reusable               (128 threads)
+    auto bar_m = [](int w, int q) { return 2u + 4u * (uint32_t)w + (uint32_t)q; };
+    static_assert(kB + 19 == kNumBarriers, "barrier count");
 
     auto wait = [&](uint32_t bar, uint32_t parity, int tag) { mbar_wait(bar, parity, tag); };
     auto arrive_leader = [&](uint32_t bar) { mbar_arrive_cluster(mapa_shared(bar, 0)); };
@@ -172,12 +171,8 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 mbar_init(p_last(b), 8);
                 mbar_init(pv_done(b), 1);
                 for (int q = 0; q < 4; ++q) mbar_init(exp_done(b, q), 1);
-                for (int q = 0; q < 4; ++q) mbar_init(m_ready(b, q), 1);
             }
             mbar_init(o_free, 8);
-            mbar_init(lm_ready(0), 4);
-            mbar_init(lm_ready(1), 4);
-            mbar_init(lm_free, 4);
             for (int i = 0; i < kKStages; ++i) {
                 mbar_init(k_full(i), 1);
                 mbar_init(k_empty(i), 1);
@@ -191,9 +186,6 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
         __syncwarp();
         tmem_alloc_2cta(smem_base + kSmemTmemPtr, kTmemCols);
         tmem_relinquish_2cta();
-    } else if (warp < 4) {
-        // row-state slots start with sequence number 0 (see the softmax loop)
-        reinterpret_cast<uint32_t*>(smem_gen + kSmemM)[threadIdx.x] = 0u;
     } else if (warp == 9 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_k);
@@ -205,9 +197,11 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
     __syncthreads();  // (orders the TMEM-address word for compute-sanitizer's racecheck, which does not model
                       // barrier.cluster; costs one CTA barrier per launch)
     tc_fence_after();
-    if (*reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr) != 0u) {
-        if (threadIdx.x == 0) printf("[fa] unexpected TMEM base address\n");
-        __trap();
+    if constexpr (kDebug) {  // (racecheck cannot order tcgen05.alloc's write of this word across the CTA pair)
+        if (*reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr) != 0u) {
+            if (threadIdx.x == 0) printf("[fa] unexpected TMEM base address\n");
+            __trap();
+        }
     }
     constexpr uint32_t tmem_base = 0u;  // all 512 columns are ours: literal keeps tcgen05 operands uniform
     const bool run = !(kDebug && dbg.level == 1u);  // bring-up level 1: setup and teardown only
@@ -429,7 +423,6 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 // only waited for at the point of use if the probe failed.
                 bool p_probed = false;
                 float m_prev = 0.f;
-                uint32_t slot_early = ((uint32_t)g & 15u) ^ 1u;  // "not yet": forces a load at the point of use
                 if constexpr (!kRagged) {
                     tmem_ld_32x32b_x32(t_s, sr[0]);
                     tmem_ld_32x32b_x32(t_s + 32, sr[1]);
@@ -437,7 +430,6 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                     tmem_wait_ld();
                     tmem_ld_32x32b_x32(t_s + 64, sr[2]);
                     tmem_ld_32x32b_x32(t_s + 96, sr[3]);
-                    if constexpr (kMSlot) slot_early = lds_volatile_u32(slot_m);  // row state of block g-1, normally there
                     m_lo = row_max_frags<0, 2>(sr);
                     tmem_wait_ld();
                 } else {
@@ -474,33 +466,11 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                 }
 
                 // ---- shared row state: the reference max of O ----
-                // Decision of block g-1 (other warpgroup, same row) published: its slot carries the block's sequence number
-                // in the four low mantissa bits of m.  Also awaited by the first block of a tile, which does not use the
-                // value: the slot has one writer at a time, in block order.
-                uint32_t slot_v = slot_early;
-                if constexpr (kMSlot) {
-#if FA_HANG_GUARD
-                    for (uint32_t spin = 0; (slot_v & 15u) != ((uint32_t)g & 15u); ++spin) {
-                        if (spin > (1u << 22)) {
-                            diag_record(0xDEAD0000u | 340u, (uint32_t)g, threadIdx.x, blockIdx.x);
-                            __trap();
-                        }
-                        slot_v = lds_volatile_u32(slot_m);
-                    }
-#else
-                    while ((slot_v & 15u) != ((uint32_t)g & 15u)) {
-                        __nanosleep(32);
-                        slot_v = lds_volatile_u32(slot_m);
-                    }
-#endif
-                } else {
-                    if (g > 0) wait(m_ready(w ^ 1, wq), (uint32_t)(((g - 1) >> 1) & 1), 340 + w);
-                    slot_v = lds_volatile_u32(slot_m);
-                }
-                m_prev = __uint_as_float(slot_v & ~15u);
-                // the candidate for the new reference max is already in its published (truncated) form, so that
-                // alpha, P and l are all computed against exactly the value the other warpgroup will read
-                mx = __uint_as_float(__float_as_uint(mx) & ~15u);
+                // Decision of block g-1 (sibling warp of the other warpgroup, same rows) published.  Also awaited by the
+                // first block of a tile, which does not use the value: the slot has one writer at a time, in block order.
+                if (g > 0) named_bar_sync(bar_m(w ^ 1, wq), 64);
+                const uint32_t slot_v = lds_volatile_u32(slot_m);
+                m_prev = __uint_as_float(slot_v);
                 float m_cur;
                 if (j == 0) {
                     m_cur = mx;  // first block of the tile: O is overwritten by PV(g) (accumulate = 0)
@@ -530,14 +500,9 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
                         l_run *= alpha;
                     }
                 }
-                // Publish: one 32-bit word per row = m with its four low mantissa bits replaced by the sequence number
-                // of the NEXT block (a single word needs no fence and no barrier; m only has to be the same value
-                // for everybody who scales against it, so the owner uses the truncated value too).
-                sts_volatile_u32(slot_m, __float_as_uint(m_cur) | ((uint32_t)(g + 1) & 15u));
-                if constexpr (!kMSlot) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(m_ready(w, wq));
-                }
+                // publish the reference max of O after this block (one word per row)
+                sts_volatile_u32(slot_m, __float_as_uint(m_cur));
+                named_bar_arrive(bar_m(w, wq), 64);  // the owner of block g+1 (sibling warp) may read it
                 m_known = m_cur;
                 have_l = true;
                 if constexpr (kDebug) {
@@ -600,10 +565,9 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
             }
 
             // hand (l_w, m_w) of this tile to the epilogue warpgroup and move on to the next tile
-            if (it > 0) wait(lm_free, (uint32_t)((it - 1) & 1), 350 + w);  // the previous tile's pair was read
+            if (it > 0) named_bar_sync(12 + w, 256);  // the previous tile's pair was read
             sm_lm[w * 128 + row] = have_l ? make_float2(l_run, m_known) : make_float2(0.f, -INFINITY);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(lm_ready(w));
+            named_bar_arrive(10 + w, 256);
         }
     } else if (wg == 3 && run) {
         // =================================== epilogue =====================================
@@ -619,11 +583,11 @@ __device__ __forceinline__ void fa_fwd_body_pp(const CUtensorMap& tm_q, const CU
         for (int it = 0; it < n_local; ++it) {
             const int g_last = (it + 1) * n_blocks - 1;
             const int w_last = g_last & 1;
-            wait(lm_ready(0), (uint32_t)(it & 1), 370);
-            wait(lm_ready(1), (uint32_t)(it & 1), 371);
+            named_bar_sync(10, 256);
+            named_bar_sync(11, 256);
             const float2 a0 = sm_lm[row], a1 = sm_lm[128 + row];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(lm_free);
+            named_bar_arrive(12, 256);
+            named_bar_arrive(13, 256);
             // O is accumulated against the last owner's reference max; the other partial sum is re-based
             const float m_fin = w_last ? a1.y : a0.y;
             const float l = a0.x * ex2_approx((a0.y - m_fin) * c) + a1.x * ex2_approx((a1.y - m_fin) * c);

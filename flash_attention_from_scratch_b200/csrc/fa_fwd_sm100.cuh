@@ -13,36 +13,32 @@
 //     epilogue of neighbouring tiles overlap.
 //   * TMA (cp.async.bulk.tensor, 128B swizzle) stages Q tiles and K/V blocks through shared
 //     memory guarded by full/empty mbarriers.
-//   * one thread issues tcgen05.mma: S_s = Q_s K_j^T (operands from smem) and O_s += P_s V_j
-//     (P read from tensor memory, V from smem, MN-major); accumulators in tensor memory.
+//   * two warps issue tcgen05.mma (one elected thread each): S_s = Q_s K_j^T (operands from smem) and
+//     O_s += P_s V_j (P read from tensor memory, V from smem, MN-major); accumulators in tensor memory.
 //   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
 //     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit in two
 //     parts (96 + 32 columns) so PV starts early, lazy rescale of O (only when the row max grew
 //     by more than 2^8), final 1/l scaling and TMA store of O through swizzled shared memory.
 //
-// Three protocols live in this file (profiles/r01_*_notes.md has the measurements behind each):
-//   generation 4b (FA_SHARED_S=0): P_s aliases S_s; S_s(j+1) is issued behind PV_s(j).
-//   generation 6  (FA_SHARED_S=1): ONE S accumulator shared by both Q tiles, P_s in its own
-//       columns; S_s(j+1) is issued as soon as the other warpgroup has read the previous S out
-//       of TMEM, i.e. while softmax_s(j) is still running.
-//   generation 7  (kPair, built on 6): two CTAs of a cluster form a tcgen05 `cta_group::2` pair.
-//       The even CTA's MMA warp issues M = 256 MMAs for both; each CTA keeps its own Q tiles,
-//       softmax and epilogue but loads only HALF of every K block (64 keys) and V block (64 of
-//       the 128 d columns): per MMA a CTA reads 6 KiB of smem operands instead of 8, and TMA
-//       writes half as much.
-//   (generation 8 -- S(j+1) prefetched into the exp2 shadow of block j -- was measured, rejected and
-//   removed again: it holds the shared accumulator longer; profiles/r01_g8_sweep.json.)
-//   generation 9  (FA_UNIFORM_WARP, FA_LD_SPLIT; both mappings): the warp index is broadcast with
-//       shfl so that ptxas keeps the MMA warp's counters and descriptors in UNIFORM registers, and
-//       the softmax warps reduce the row max of S[:, :64] while S[:, 64:] is still being fetched.
-//       Why: a tensor-pipe observer (tools/gpu_trace.py) showed every QK^T group occupying the pipe
-//       for ~930 clk instead of 512, tools/mma_probe.cu showed that no interference (register math,
-//       bulk copies, tcgen05.ld, random operands, group alternation) slows a tcgen05.mma down, and
-//       switching the softmax arithmetic / TMA / S read-out off in the debug kernel changed nothing:
-//       the time went into ~26 R2UR per group that ptxas placed between the barrier wait and the
-//       first UTCHMMA because it could not prove the issuing warp's values uniform.  With the hint
-//       the single-CTA mapping gained 13 % (1279 -> 1450 TFLOP/s), the pair 2 % (1431 -> 1459)
-//       (profiles/r01_g9_notes.md).
+// History (profiles/r01_*_notes.md, profiles/r02_pp_notes.md have the measurements behind each step; the
+// losing protocols are gone from this file, their patches are archived under profiles/):
+//   generation 6: ONE S accumulator shared by both Q tiles, P_s in its own tensor-memory columns; S_s(j+1) is
+//       issued as soon as the other warpgroup has read the previous S out, i.e. while softmax_s(j) is running.
+//   generation 7 (kPair): two CTAs of a cluster form a tcgen05 `cta_group::2` pair.  The even CTA issues M = 256
+//       MMAs for both; each CTA keeps its own Q tiles, softmax and epilogue but loads only HALF of every K block
+//       (64 keys) and V block (64 of the 128 d columns): 6 KiB instead of 8 KiB of smem operands per MMA.
+//   generation 9 (FA_UNIFORM_WARP, FA_LD_SPLIT): the warp index is broadcast with shfl so that ptxas keeps the
+//       issuing warps' counters and descriptors in UNIFORM registers (without it ~26 R2UR sat between every
+//       barrier wait and the first UTCHMMA: +13 % single, +2 % pair), and the softmax warps reduce the row max of
+//       S[:, :64] while S[:, 64:] is still being fetched.
+//   generation 14: TWO MMA-issuing warps (warp 8: the QK^T groups, warp 10: the PV groups) and separate K and V
+//       rings.  A cycle trace of the ping-pong kernel (fa_fwd_pp_sm100.cuh) showed one in-order issuing warp
+//       needing ~1400 clk of its own instruction time per KV block -- mbarrier waits at ~90 clk even when long
+//       complete, ~25-30 clk per tcgen05.mma, commits -- and in this kernel that time sits inside the serial
+//       chain through the shared S accumulator (pair kernel +2 % at seq_len >= 8192, single +10 % at 512).
+//   Removed after measurement: generation 4b (P aliased onto per-tile S, FlashAttention-4's layout: 1399 vs 1450),
+//   generation 8 (S prefetched into the exp2 shadow), generation 10 (S in 64-column halves), generation 11 (P
+//   through shared memory: 1422 vs 1464, shared-memory bandwidth).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -101,17 +97,8 @@ static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
-#ifndef FA_SHARED_S
-#define FA_SHARED_S 1         // single-CTA kernel: 1 = generation 6, 0 = generation 4b (see top of file)
-#endif
-constexpr bool kSharedSDefault = FA_SHARED_S != 0;
-#ifndef FA_DUAL_ISSUE
-#define FA_DUAL_ISSUE 1       // generation 14 (shared-S protocols): TWO MMA-issuing warps -- warp 8 streams the QK^T
-                              // groups, warp 10 the PV groups -- and separate K and V rings.  A cycle trace of the
-                              // ping-pong kernel (profiles/r02_pp_notes.md) showed that ONE in-order issuing warp
-                              // needs ~1400 clk of its own instruction time per KV block (mbarrier waits at ~90 clk
-                              // even when long complete, ~25-30 clk per tcgen05.mma, commits): in this kernel that
-                              // time sits inside the serial chain through the shared S accumulator.
+#ifndef FA_QK_ONE_ASM
+#define FA_QK_ONE_ASM 1       // CTA-pair kernel: a QK^T group is one asm statement (see umma_ss_2cta_k8)
 #endif
 #ifndef FA_UNIFORM_WARP
 #define FA_UNIFORM_WARP 1
@@ -123,17 +110,10 @@ constexpr bool kSharedSDefault = FA_SHARED_S != 0;
 #endif
 static_assert(kKVStages >= 4, "generation 6/7 keep V_j, K_j+1, V_j+1, K_j+2 in flight");
 
-// Tensor-memory column map (512 columns, base 0).
-//   generation 6/7: [0,64) P_0   [64,128) P_1   [128,256) S (shared)   [256,384) O_0   [384,512) O_1
-//   generation 4b:  [0,128) S_0/P_0   [128,256) S_1/P_1                 [256,384) O_0   [384,512) O_1
-template <bool kSharedS>
-__host__ __device__ constexpr uint32_t tmem_col_s(int s) {
-    return kSharedS ? 128u : static_cast<uint32_t>(s) * 128u;
-}
-template <bool kSharedS>
-__host__ __device__ constexpr uint32_t tmem_col_p(int s) {
-    return kSharedS ? static_cast<uint32_t>(s) * 64u : static_cast<uint32_t>(s) * 128u;
-}
+// Tensor-memory column map (512 columns, base 0):
+//   [0,64) P_0   [64,128) P_1   [128,256) S (shared by both Q tiles)   [256,384) O_0   [384,512) O_1
+__host__ __device__ constexpr uint32_t tmem_col_s() { return 128u; }
+__host__ __device__ constexpr uint32_t tmem_col_p(int s) { return static_cast<uint32_t>(s) * 64u; }
 __host__ __device__ constexpr uint32_t tmem_col_o(int s) {
     return 256u + static_cast<uint32_t>(s) * 128u;
 }
@@ -182,9 +162,7 @@ template <bool kBF16, bool kDebug, bool kRagged, bool kPair>
 __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUtensorMap& tm_k,
                                             const CUtensorMap& tm_v, const CUtensorMap& tm_o,
                                             const FwdParams& prm, const FwdDebug& dbg) {
-    constexpr bool kSharedS = kPair || kSharedSDefault;
     constexpr bool kLdSplit = !kRagged && (FA_LD_SPLIT != 0);
-    constexpr bool kDual = kSharedS && (FA_DUAL_ISSUE != 0);
     constexpr int kStages = kPair ? 2 * kKVStages : kKVStages;  // K/V ring slots ...
     constexpr int kSlotBytes = kPair ? kTileBytes / 2 : kTileBytes;  // ... of this size
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
@@ -192,9 +170,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     constexpr int kRowsPerTile = (kPair ? 2 : 1) * kQStages * kBlockM;
     constexpr int kSmemO = kSmemStage;        // O staging of Q tile 0 ...
     constexpr int kSmemOStride = kHalfBytes;  // ... and the step to tile 1
-    auto col_s = [](int s) -> uint32_t {  // tensor-memory column of the S accumulator of Q tile s
-        return tmem_col_s<kPair || kSharedSDefault>(s);
-    };
+    auto col_s = [](int) -> uint32_t { return tmem_col_s(); };  // one S accumulator for both Q tiles
 
     // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, which makes every
     // shared-memory address below a link-time constant instead of a live register.
@@ -233,7 +209,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     auto s_full = [&](int s) { return bar0 + 8u * (4 + 2 * kMaxStages + s); };
     auto p_full = [&](int s) { return bar0 + 8u * (6 + 2 * kMaxStages + s); };
     auto p_last = [&](int s) { return bar0 + 8u * (8 + 2 * kMaxStages + s); };
-    auto o_full = [&](int s) { return bar0 + 8u * (10 + 2 * kMaxStages + s); };  // generation 4b only
     auto o_free = [&](int s) { return bar0 + 8u * (12 + 2 * kMaxStages + s); };
     const uint32_t s_free = bar0 + 8u * (14 + 2 * kMaxStages);                   // generation 6/7
     auto pv_done = [&](int s) { return bar0 + 8u * (15 + 2 * kMaxStages + s); };  // generation 6/7
@@ -280,7 +255,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 mbar_init(s_full(s), 1);
                 mbar_init(p_full(s), kArrivals);  // one elected arrive per softmax warp
                 mbar_init(p_last(s), kArrivals);
-                mbar_init(o_full(s), 1);
                 mbar_init(o_free(s), kArrivals);
                 mbar_init(pv_done(s), 1);
             }
@@ -312,9 +286,13 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     tc_fence_after();
     // All 512 TMEM columns are allocated by the only CTA on this SM, so the base address is 0.
     // Using the literal keeps every tcgen05 operand warp-uniform (no R2UR per MMA).
-    if (*reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr) != 0u) {
-        if (threadIdx.x == 0) printf("[fa] unexpected TMEM base address\n");
-        __trap();
+    // (checked in the debug instantiation, which tests/test_kernel_gpu.py runs in every mapping: in a CTA pair
+    // compute-sanitizer's racecheck cannot order tcgen05.alloc's write of this word against a read)
+    if constexpr (kDebug || !kPair) {
+        if (*reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemTmemPtr) != 0u) {
+            if (threadIdx.x == 0) printf("[fa] unexpected TMEM base address\n");
+            __trap();
+        }
     }
     constexpr uint32_t tmem_base = 0u;
 
@@ -349,11 +327,11 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     __syncwarp();
                 };
                 auto load_kv = [&](bool is_k, int blk) {
-                    // kDual: K blocks cycle through the first half of the slots, V blocks through the second
-                    // (item = 2 * block + is_v, running across tiles); else one ring in consumption order
+                    // K blocks cycle through the first half of the slots, V blocks through the second
+                    // (item = 2 * block + is_v, running across tiles): the two MMA-issuing warps each own a ring
                     constexpr int kH = kStages / 2;
-                    const int slot = kDual ? (is_k ? 0 : kH) + (item >> 1) % kH : item % kStages;
-                    const uint32_t use = kDual ? (uint32_t)((item >> 1) / kH) : (uint32_t)(item / kStages);
+                    const int slot = (is_k ? 0 : kH) + (item >> 1) % kH;
+                    const uint32_t use = (uint32_t)((item >> 1) / kH);
                     wait(kv_empty(slot), (use & 1u) ^ 1u, 100 + slot);
                     if (kDebug && level >= 7 && use > 0) {
                         // ablation: keep the barrier protocol, skip the copy (the slot keeps old data)
@@ -395,7 +373,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             // (profiles/r01_v4_trace_notes.md).
             constexpr int kM = kPair ? 2 * kBlockM : kBlockM;
             constexpr uint32_t idesc_qk = umma_idesc_f16(kBF16, kM, kBlockN, false);
-            constexpr uint32_t idesc_pv = umma_idesc_f16(kBF16, kM, kHeadDim, true);
             // Q/K tiles: K-major, 8-row x 128 B swizzle atoms 1024 B apart (SBO); LBO unused.
             // V tiles: MN-major; next 64-wide d chunk 16 KiB away (LBO), next 8 kv rows 1 KiB
             // (SBO); one k-step = 16 kv rows = 2 KiB.  P (A operand in TMEM): 8 columns/k-step.
@@ -404,11 +381,12 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             auto k_desc = [&](int slot) {
                 return umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, 16, 1024);
             };
-            auto v_desc = [&](int slot) {
-                return umma_smem_desc_sw128(smem_base + kSmemKV + slot * kSlotBytes, kHalfBytes, 1024);
-            };
             auto issue_qk_b = [&](int s, uint64_t b0) {
                 const uint64_t a0 = umma_smem_desc_sw128(smem_base + kSmemQ + s * kTileBytes, 16, 1024);
+                if constexpr (kPair && FA_QK_ONE_ASM) {
+                    umma_ss_2cta_k8<(kHalfBytes >> 4), (kKHalfBytes >> 4)>(tmem_base + col_s(s), a0, b0, idesc_qk);
+                    return;
+                }
 #pragma unroll
                 for (int k = 0; k < kHeadDim / 16; ++k) {
                     const uint32_t a_off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
@@ -419,24 +397,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         umma_ss(tmem_base + col_s(s), a0 + a_off, b0 + b_off, idesc_qk, k > 0);
                 }
             };
-            auto issue_qk = [&](int s, int slot) { issue_qk_b(s, k_desc(slot)); };
-            auto issue_pv_b = [&](int s, uint64_t b0, bool accumulate, int k_begin, int k_end) {
-#pragma unroll
-                for (int k = k_begin; k < k_end; ++k) {
-                    const uint32_t acc = (accumulate || k > 0) ? 1u : 0u;
-                    if constexpr (kPair)
-                        umma_ts_2cta(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
-                                     b0 + ((k * 2048) >> 4), idesc_pv, acc);
-                    else
-                        umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
-                                b0 + ((k * 2048) >> 4), idesc_pv, acc);
-                }
-            };
-            auto issue_pv = [&](int s, int slot, bool accumulate, int k_begin, int k_end) {
-                issue_pv_b(s, v_desc(slot), accumulate, k_begin, k_end);
-            };
-            auto slot_of = [&](int i) { return i % kStages; };
-            auto parity_of = [&](int i) { return (uint32_t)((i / kStages) & 1); };
 
             if constexpr (kDebug) {
                 if (level == 2) {  // raw smem images of Q_0 and K_0 as TMA wrote them
@@ -451,7 +411,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                 }
             }
-            if constexpr (kDual) {
+            {
                 // ------------- generation 14: this warp streams the QK^T groups only -------------
                 //   S_0(0) S_1(0) S_0(1) S_1(1) ...   each into the shared accumulator as soon as the previous S was
                 //   read out (`s_free`) and K_j landed; the PV groups are issued by warp 10.
@@ -481,192 +441,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                     }
                 }
-            } else if constexpr (kSharedS) {
-                // ------------- generation 6 / 7: one shared S accumulator -------------
-                // Issue order per work tile (n = n_blocks):
-                //   S_0(0) S_1(0) S_0(1) | PV_0(0) S_1(1) PV_1(0) S_0(2) | PV_0(1) S_1(2) PV_1(1) S_0(3) ...
-                // Every S waits for `s_free` (the other warpgroup has read the previous S out of
-                // TMEM), every PV_s(j) for P_s(j).  S_s(j+1) is therefore produced while
-                // softmax_s(j) is still running.
-                int base = 0;     // ring item of this tile's K_0 (K_j = base + 2j, V_j = base + 2j + 1)
-                uint32_t u = 0;   // S accumulators issued so far (all tiles): s_free parity
-                uint32_t g0 = 0;  // KV blocks of earlier tiles: parity base of s/p/pv barriers
-                int it = 0;
-                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
-                    auto trace_ptr = [&](int j, int s, int off) -> uint32_t* {
-                        if constexpr (kDebug) {
-                            if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
-                                j < 32 && lane == 0)
-                                return reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + off +
-                                       (j * 2 + s) * 4;
-                        }
-                        return nullptr;
-                    };
-                    auto issue_s = [&](int s, int jj) {  // S = Q_s K_jj^T into the shared accumulator
-                        uint32_t* tr = trace_ptr(jj, s, 768);
-                        const int itk = base + 2 * jj;
-                        const uint64_t kd = k_desc(slot_of(itk));
-                        if constexpr (kDebug) {
-                            if (tr) tr[0] = clk32();
-                        }
-                        wait(kv_full(slot_of(itk)), parity_of(itk), 200);
-                        if (jj == 0) wait(q_full(s), (uint32_t)(it & 1), 210 + s);
-                        if (u > 0) wait(s_free, (u - 1u) & 1u, 270 + s);
-                        if constexpr (kDebug) {
-                            if (tr) tr[1] = clk32();
-                        }
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_qk_b(s, kd);
-                            commit(s_full(s));
-                            if (jj + 1 == n_blocks) commit(q_empty(s));  // last use of Q_s
-                            if (s == 1) commit(kv_empty(slot_of(itk)));  // both tiles used K_jj
-                        }
-                        __syncwarp();
-                        if constexpr (kDebug) {
-                            if (tr) tr[2] = clk32();
-                        }
-                        ++u;
-                    };
-                    auto issue_o = [&](int s, int j) {  // O_s (+)= P_s(j) V_j
-                        uint32_t* tr = trace_ptr(j, s, 512);
-                        const int itv = base + 2 * j + 1;
-                        const uint64_t vd = v_desc(slot_of(itv));
-                        const uint32_t par = (g0 + (uint32_t)j) & 1u;
-                        wait(kv_full(slot_of(itv)), parity_of(itv), 220);
-                        wait(p_full(s), par, 230 + s);  // P_s(j) stored, O_s rescaled
-                        if constexpr (kDebug) {
-                            if (tr) tr[0] = clk32();
-                        }
-                        if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
-                            wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
-                        tc_fence_after();
-                        if constexpr (kSplitP) {
-                            if (elect_one()) issue_pv_b(s, vd, j > 0, 0, 6);
-                            __syncwarp();
-                            if constexpr (kDebug) {
-                                if (tr) tr[1] = clk32();
-                            }
-                            wait(p_last(s), par, 250 + s);  // last 32 columns of P_s(j)
-                            if constexpr (kDebug) {
-                                if (tr) tr[2] = clk32();
-                            }
-                            tc_fence_after();
-                            if (elect_one()) {
-                                issue_pv_b(s, vd, true, 6, 8);
-                                commit(pv_done(s));
-                                if (s == 1) commit(kv_empty(slot_of(itv)));
-                            }
-                            __syncwarp();
-                        } else {
-                            if (elect_one()) {
-                                issue_pv_b(s, vd, j > 0, 0, 8);
-                                commit(pv_done(s));
-                                if (s == 1) commit(kv_empty(slot_of(itv)));
-                            }
-                            __syncwarp();
-                        }
-                        if constexpr (kDebug) {
-                            if (tr) tr[3] = clk32();
-                        }
-                    };
-                    issue_s(0, 0);
-                    issue_s(1, 0);
-                    if (level >= 4) {
-                        if (n_blocks > 1) issue_s(0, 1);
-                        for (int j = 0; j < n_blocks; ++j) {
-                            issue_o(0, j);
-                            if (j + 1 < n_blocks) issue_s(1, j + 1);
-                            issue_o(1, j);
-                            if (j + 2 < n_blocks) issue_s(0, j + 2);
-                        }
-                    }
-                    base += 2 * n_blocks;
-                    g0 += (uint32_t)n_blocks;
-                }
-            } else {
-                // ------------------------------ generation 4b ------------------------------
-                int item = 0;    // K/V ring item counter, same order as the producer
-                uint32_t g = 0;  // KV blocks processed so far (all tiles): parity of s/p barriers
-                int it = 0;
-                for (int tile = cta_lin; level >= 3 && tile < tile_end; tile += n_cta, ++it) {
-                    // prologue: S_s(0) = Q_s K_0^T.  S_s is free: the PV that consumed the previous
-                    // tile's last P_s was issued before (in-order tensor pipe).
-                    wait(kv_full(slot_of(item)), parity_of(item), 200);
-                    for (int s = 0; s < kQStages; ++s) {
-                        wait(q_full(s), (uint32_t)(it & 1), 210 + s);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_qk(s, slot_of(item));
-                            commit(s_full(s));
-                            if (n_blocks == 1) commit(q_empty(s));
-                        }
-                        __syncwarp();
-                    }
-                    if (elect_one()) commit(kv_empty(slot_of(item)));
-                    __syncwarp();
-                    ++item;
-                    for (int j = 0; level >= 4 && j < n_blocks; ++j, ++g) {
-                        const int it_v = item;      // V_j
-                        const int it_k = item + 1;  // K_{j+1}
-                        const bool has_next = (j + 1 < n_blocks);
-                        wait(kv_full(slot_of(it_v)), parity_of(it_v), 220);
-                        for (int s = 0; s < kQStages; ++s) {
-                            uint32_t* tr = nullptr;
-                            if constexpr (kDebug) {
-                                if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 &&
-                                    j < 32 && lane == 0)
-                                    tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 512 +
-                                         (j * 2 + s) * 4;
-                            }
-                            wait(p_full(s), g & 1u, 230 + s);  // P_s(j) stored, O_s rescaled
-                            if constexpr (kDebug) {
-                                if (tr) tr[0] = clk32();
-                            }
-                            if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
-                                wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
-                            tc_fence_after();
-                            if (elect_one()) issue_pv(s, slot_of(it_v), j > 0, 0, kSplitP ? 6 : 8);
-                            __syncwarp();
-                            if constexpr (kDebug) {
-                                if (tr) tr[1] = clk32();
-                            }
-                            if constexpr (kSplitP) {
-                                wait(p_last(s), g & 1u, 250 + s);  // last 32 columns of P_s(j)
-                                tc_fence_after();
-                            }
-                            if constexpr (kDebug) {
-                                if (tr) tr[2] = clk32();
-                            }
-                            if (has_next && s == 0) {
-                                wait(kv_full(slot_of(it_k)), parity_of(it_k), 240);
-                                tc_fence_after();
-                            }
-                            if (elect_one()) {
-                                if constexpr (kSplitP) issue_pv(s, slot_of(it_v), true, 6, 8);
-                                if (has_next) {
-                                    issue_qk(s, slot_of(it_k));
-                                    commit(s_full(s));
-                                    if (j + 2 == n_blocks) commit(q_empty(s));  // last use of Q_s
-                                } else {
-                                    commit(o_full(s));
-                                }
-                            }
-                            __syncwarp();
-                            if constexpr (kDebug) {
-                                if (tr) tr[3] = clk32();
-                            }
-                        }
-                        if (elect_one()) {
-                            commit(kv_empty(slot_of(it_v)));
-                            if (has_next) commit(kv_empty(slot_of(it_k)));
-                        }
-                        __syncwarp();
-                        item += has_next ? 2 : 1;
-                    }
-                }
             }
-        } else if (kDual && warp == 10 && is_leader) {
+        } else if (warp == 10 && is_leader) {
             // ======================= MMA issuer 2 (generation 14): the PV groups =======================
             //   PV_0(0) PV_1(0) PV_0(1) PV_1(1) ...   each as soon as P_s(j) is stored (96 + 32 keys) and V_j landed
             constexpr int kM = kPair ? 2 * kBlockM : kBlockM;
@@ -689,14 +465,22 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                             wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
                         tc_fence_after();
                         auto pv = [&](int k_begin, int k_end) {
+                            if constexpr (kPair && kSplitP && FA_QK_ONE_ASM) {  // one asm statement per part
+                                if (k_begin == 0)
+                                    umma_ts_2cta_k0to5(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s), vd, idesc_pv,
+                                                       j > 0 ? 1u : 0u);
+                                else
+                                    umma_ts_2cta_k6to7(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s), vd, idesc_pv);
+                                return;
+                            }
 #pragma unroll
                             for (int k = k_begin; k < k_end; ++k) {
                                 const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
                                 if constexpr (kPair)
-                                    umma_ts_2cta(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                    umma_ts_2cta(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s) + k * 8,
                                                  vd + ((k * 2048) >> 4), idesc_pv, acc);
                                 else
-                                    umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p<kSharedS>(s) + k * 8,
+                                    umma_ts(tmem_base + tmem_col_o(s), tmem_base + tmem_col_p(s) + k * 8,
                                             vd + ((k * 2048) >> 4), idesc_pv, acc);
                             }
                         };
@@ -716,32 +500,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 }
                 g0 += (uint32_t)n_blocks;
             }
-        } else if (warp == 10) {
-            // ====================== tensor-pipe observer (cycle trace only) ======================
-            // Level 5: an otherwise idle warp watches the completion barriers of the first work tile
-            // in the order the in-order tensor pipe retires the groups,
-            //     S_0(j)  PV_0(j-1)  S_1(j)  PV_1(j-1)        (j >= 1),
-            // so the deltas between consecutive stamps are the pipe time of each 8-MMA group while
-            // the pipe is backlogged.  Bounded polls: a missed phase gives a zero, never a hang.
-            if constexpr (kDebug && kSharedS) {
-                if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && lane == 0 && cta_lin < tile_end) {
-                    uint32_t* ob = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 1024;
-                    auto stamp = [&](uint32_t bar, uint32_t parity) -> uint32_t {
-                        for (int spin = 0; spin < (1 << 20); ++spin)
-                            if (mbar_try_wait(bar, parity)) return clk32();
-                        return 0u;
-                    };
-                    const int nb = min(n_blocks, 32);
-                    ob[0] = stamp(s_full(0), 0u);
-                    ob[2] = stamp(s_full(1), 0u);
-                    for (int j = 1; j < nb; ++j) {
-                        ob[j * 4 + 0] = stamp(s_full(0), (uint32_t)j & 1u);
-                        ob[j * 4 + 1] = stamp(pv_done(0), (uint32_t)(j - 1) & 1u);
-                        ob[j * 4 + 2] = stamp(s_full(1), (uint32_t)j & 1u);
-                        ob[j * 4 + 3] = stamp(pv_done(1), (uint32_t)(j - 1) & 1u);
-                    }
-                }
-            }
         }
         __syncwarp();
     } else {
@@ -751,7 +509,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
         const int row = threadIdx.x & 127;   // row inside the tile == TMEM lane
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t t_s = tmem_base + lane_sel + col_s(s);
-        const uint32_t t_p = tmem_base + lane_sel + tmem_col_p<kSharedS>(s);
+        const uint32_t t_p = tmem_base + lane_sel + tmem_col_p(s);
         const uint32_t t_o = tmem_base + lane_sel + tmem_col_o(s);
         const float c = prm.scale_log2;
         const int kv_tail = prm.seq_len & (kBlockN - 1);  // valid keys in the last block (0 = all)
@@ -802,20 +560,20 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_s + q * 32, sr[q]);
                     tmem_wait_ld();
                 }
-                if constexpr (kSharedS) {
-                    // S is in registers: hand the shared accumulator to the other Q tile's next S
-                    tc_fence_before();
-                    __syncwarp();
-                    if constexpr (kLdSplit) {
-                        // ptxas hoists the arrive (and with it the stall on the last tcgen05.ld)
-                        // above the reduction of the first half; a never-true dependency on m_lo
-                        // keeps it behind
-                        const uint32_t skew = (__float_as_uint(m_lo) == 0x7fc12345u) ? 8u : 0u;
-                        if (lane == 0) arrive_leader(s_free + skew);
-                    } else {
-                        if (lane == 0) arrive_leader(s_free);
-                    }
+                // S is in registers: hand the shared accumulator to the other Q tile's next S
+                tc_fence_before();
+                __syncwarp();
+                if constexpr (kLdSplit) {
+                    // ptxas hoists the arrive (and with it the stall on the last tcgen05.ld) above the reduction of
+                    // the first half; a never-true dependency on m_lo keeps it behind.  Never true: m_lo comes out
+                    // of an FMNMX chain, whose only NaN result is the canonical 0x7fffffff (one input NaN -> the
+                    // other input; both NaN -> canonical NaN), never this payload.
+                    const uint32_t skew = (__float_as_uint(m_lo) == 0x7fc12345u) ? 8u : 0u;
+                    if (lane == 0) arrive_leader(s_free + skew);
+                } else {
+                    if (lane == 0) arrive_leader(s_free);
                 }
+                
                 if constexpr (kDebug) {
                     if (tr) tr[1] = clk32();
                 }
@@ -855,10 +613,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                         // O_s must be quiescent.  Generation 4b: S_s(j) was committed after
                         // PV_s(j-1); generation 6/7: wait for PV_s(j-1) explicitly.
-                        if constexpr (kSharedS) {
-                            wait(pv_done(s), (g - 1u) & 1u, 320 + s);
-                            tc_fence_after();
-                        }
+                                wait(pv_done(s), (g - 1u) & 1u, 320 + s);
+                        tc_fence_after();
+                    
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint32_t o[32];
@@ -889,20 +646,19 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     } else {
                         exp_fragment<kBF16, kEmuPairs, FA_EXP_VARIANT>(sr[q], c2, nm2, sum_a, sum_b, pk);
                     }
-                    if constexpr (kSharedS) {
                         // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued about one
-                        // softmax fragment ago, so this rarely spins)
-                        if (q == 0 && j > 0) {
-                            if constexpr (kDebug) {
-                                if (tr) tr[5] = clk32();
-                            }
-                            wait(pv_done(s), (g - 1u) & 1u, 330 + s);
-                            tc_fence_after();
-                            if constexpr (kDebug) {
-                                if (tr) tr[6] = clk32();
-                            }
+                    // softmax fragment ago, so this rarely spins)
+                    if (q == 0 && j > 0) {
+                        if constexpr (kDebug) {
+                            if (tr) tr[5] = clk32();
+                        }
+                        wait(pv_done(s), (g - 1u) & 1u, 330 + s);
+                        tc_fence_after();
+                        if constexpr (kDebug) {
+                            if (tr) tr[6] = clk32();
                         }
                     }
+                
                     tmem_st_32x32b_x16(t_p + q * 16, pk);
                     if (kSplitP && q == 2) {
                         tmem_wait_st();
@@ -926,8 +682,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
 
             // ------------------------------- epilogue ------------------------------------
             if (level >= 4) {
-                if constexpr (kSharedS) wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
-                else wait(o_full(s), (uint32_t)(it & 1), 310 + s);
+                wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
                 tc_fence_after();
                 const float inv_l = 1.0f / l_run;
                 if constexpr (kDebug) {

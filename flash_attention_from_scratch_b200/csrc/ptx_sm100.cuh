@@ -365,6 +365,70 @@ __device__ __forceinline__ void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, u
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One QK^T group (8 MMAs, K = 128) as ONE asm statement: the per-k descriptors are derived from the two base
+// descriptors inside the PTX, so the compiler has 4 operands to place in uniform registers instead of 8 x 5 (with
+// eight separate statements ptxas ran out of uniform registers in the CTA-pair kernel and moved 26 values through
+// vector registers -- R2UR -- between the barrier wait and the first UTCHMMA of every group).
+// kAHalf / kBHalf: descriptor distance (bytes >> 4) between the two 64-column halves of the A / B tile.
+template <int kAHalf, int kBHalf>
+__device__ __forceinline__ void umma_ss_2cta_k8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "add.s64 a, %1, 2;\n\tadd.s64 b, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, 4;\n\tadd.s64 b, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, 6;\n\tadd.s64 b, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, %4;\n\tadd.s64 b, %2, %5;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, %6;\n\tadd.s64 b, %2, %7;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, %8;\n\tadd.s64 b, %2, %9;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t"
+        "add.s64 a, %1, %10;\n\tadd.s64 b, %2, %11;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(kAHalf), "n"(kBHalf), "n"(kAHalf + 2),
+        "n"(kBHalf + 2), "n"(kAHalf + 4), "n"(kBHalf + 4), "n"(kAHalf + 6), "n"(kBHalf + 6)
+        : "memory");
+}
+// The PV group of one KV block in two asm statements (keys [0,96) and [96,128): the second waits for the last
+// part of P): A = P in tensor memory (8 columns per k-step), B = V in shared memory (MN-major: 2 KiB = 128
+// descriptor units per k-step).  `accumulate` applies to the very first MMA only (0: O is overwritten).
+__device__ __forceinline__ void umma_ts_2cta_k0to5(uint32_t d_tmem, uint32_t p_tmem, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 b;\n\t.reg .b32 a;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "add.u32 a, %1, 8;\n\tadd.s64 b, %2, 128;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t"
+        "add.u32 a, %1, 16;\n\tadd.s64 b, %2, 256;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t"
+        "add.u32 a, %1, 24;\n\tadd.s64 b, %2, 384;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t"
+        "add.u32 a, %1, 32;\n\tadd.s64 b, %2, 512;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t"
+        "add.u32 a, %1, 40;\n\tadd.s64 b, %2, 640;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(p_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_2cta_k6to7(uint32_t d_tmem, uint32_t p_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 b;\n\t.reg .b32 a;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "add.u32 a, %1, 48;\n\tadd.s64 b, %2, 768;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t"
+        "add.u32 a, %1, 56;\n\tadd.s64 b, %2, 896;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], b, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(p_tmem), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
 // Arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once all
 // tcgen05 ops issued so far by this thread (for the CTA pair) have retired.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {

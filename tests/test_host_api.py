@@ -40,6 +40,47 @@ def test_library_is_sm100a_with_tcgen05_and_tma(lib):
     assert re.search(r"(?<![A-Z])HMMA\.", sass) is None  # no legacy mma.sync path
 
 
+PRODUCTION_KERNELS = {  # bf16, aligned shapes: the instantiations bench.py times
+    "pair": "_ZN2fa18fa_fwd_kernel_pairILb1ELb0ELb0EEEv14CUtensorMap_stS1_S1_S1_NS_9FwdParamsENS_8FwdDebugE",
+    "single": "_ZN2fa13fa_fwd_kernelILb1ELb0ELb0EEEv14CUtensorMap_stS1_S1_S1_NS_9FwdParamsENS_8FwdDebugE",
+    "pingpong": "_ZN2fa2pp16fa_fwd_kernel_ppILb1ELb0ELb0EEEv14CUtensorMap_stS2_S2_S2_NS_9FwdParamsENS_8FwdDebugE",
+}
+
+
+@pytest.mark.parametrize("kernel,n_mma,max_r2ur,max_r2ur_before_mma", [("pair", 32, 100, 16), ("single", 32, 64, 12),
+                                                                       ("pingpong", 16, 44, 12)])
+def test_sass_properties_the_speed_depends_on(lib, kernel, n_mma, max_r2ur, max_r2ur_before_mma):
+    """What a toolkit bump could silently undo: the issuing warps' operands must live in UNIFORM
+    registers.  Generation 9 found ~26 R2UR (vector -> uniform moves) between every barrier wait and the first
+    UTCHMMA of a group to be the pacing item of the whole kernel; generation 14 found the same pattern coming back
+    in the CTA-pair kernel when ptxas ran out of uniform registers (fixed with one asm statement per MMA group).
+    Pinned here, on the SASS of the in-tree library: no spills, the number of tcgen05.mma issue sites, the total
+    R2UR count and the R2UR count between the last SYNCS...TRYWAIT and the first UTCHMMA of every issue group."""
+    from flash_attention_from_scratch_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", PRODUCTION_KERNELS[kernel], str(_lib.lib_path())],
+                          capture_output=True, text=True).stdout
+    ops = [re.sub(r"/\*[0-9a-f]+\*/", "", ln).strip().split(";")[0].strip()
+           for ln in sass.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln)]
+    assert len(ops) > 1000, "kernel not found in the library"
+    assert not any(o.startswith(("STL", "LDL")) for o in ops), "register spills"
+    assert sum("UTCHMMA" in o for o in ops) == n_mma
+    assert sum(o.startswith("R2UR") for o in ops) <= max_r2ur
+    worst, since, in_group = 0, None, False
+    for o in ops:
+        if "SYNCS.PHASECHK" in o:
+            since, in_group = 0, False
+        elif "UTCHMMA" in o:
+            if not in_group and since is not None:
+                worst = max(worst, since)
+            in_group = True
+        elif since is not None and not in_group and o.startswith("R2UR"):
+            since += 1
+    assert worst <= max_r2ur_before_mma, worst
+    for mnemonic in ("UTMALDG", "UTMASTG", "LDTM", "STTM", "MUFU.EX2", "FFMA2"):
+        assert any(mnemonic in o for o in ops), mnemonic
+
+
 def test_kernel_info(lib):
     from flash_attention_from_scratch_b200 import _lib
 

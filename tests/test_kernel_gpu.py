@@ -116,6 +116,25 @@ def test_every_machine_mapping(mode, dtype, B, N, H):
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=atol)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_debug_instantiation_setup_and_full_run(lib, mode):
+    """The debug instantiation asserts what the production kernels assume without looking (tensor-memory base
+    address 0, 1024-byte aligned dynamic shared memory): level 1 = set-up and tear-down only, level 4 = the whole
+    kernel, in every machine mapping."""
+    q, k, v = rand_qkv((1, 384, 2, 128), torch.bfloat16, seed=3)
+    o = torch.zeros_like(q)
+    dump = torch.zeros(2 * 128 * 128 + 512 + 1024, dtype=torch.float32).pin_memory()
+    diag = torch.zeros(256, dtype=torch.int32).pin_memory()
+    sb, sn, sh, _ = q.stride()
+    with kernel_mode(mode):
+        for level in (1, 4):
+            knobs = (C.c_uint32 * 8)(0, 0, 0, 0, 0, 0, 0, level)
+            rc = lib.fa_fwd_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), 1, 384, 2, 128, sb, sn, sh,
+                                  15, dump.data_ptr(), knobs, diag.data_ptr())
+            assert rc == 0, (mode, level)
+    torch.testing.assert_close(o.float(), sdpa32(q, k, v), rtol=1e-2, atol=2e-3)
+
+
 def test_kernel_cfg_selects_the_machine_mapping_per_call():
     """kernel_cfg.cta_group = 1 / 2 picks single CTAs / CTA pairs for that call only (thread-local
     override in the library); every config of the tuning grid reproduces the AUTO result."""

@@ -30,9 +30,8 @@ VARIANTS = {
     "nosplit": {"FA_SPLIT_P": 0},
     "pptoken": {"FA_PP_TOKEN": 1},         # ping-pong kernel with the exp2-phase token
     "ppnoskew": {"FA_PP_SKEW_NS": 0},
-    "nodual": {"FA_DUAL_ISSUE": 0},        # generation 9: one MMA-issuing warp, one K/V ring
+    "noasm": {"FA_QK_ONE_ASM": 0},         # CTA-pair kernel: one asm statement per tcgen05.mma instead of per group
     "ppnoprobe": {"FA_PP_PROBE": 0},
-    "ppmslot": {"FA_PP_MSLOT": 1},         # reference max handed over as a sequence-stamped word (no mbarrier)
     "ppexpv1": {"FA_EXP_VARIANT": 1},
     "hint": {"FA_WAIT_HINT": 10000000},   # CUTLASS-style 10 ms suspend-time hint on every try_wait
     "sleep32": {"FA_WAIT_SLEEP": 32},     # nanosleep back-off in the wait loops
