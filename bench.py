@@ -241,7 +241,6 @@ def run_reference(args, rank, world):
 
 
 def main():
-    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     # 50 back-to-back launches = 40 ms at the headline.  The board is power-capped under this kernel, so
@@ -261,7 +260,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     if "WORLD_SIZE" not in os.environ and args.gpus > 1:
-        respawn_under_torchrun(args.gpus)
+        respawn_under_torchrun(args.gpus)  # (before stdout is claimed: the ranks inherit the descriptors)
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
