@@ -61,13 +61,18 @@ constexpr int kKVStages = FA_KV_STAGES;  // K/V ring slots of 32 KiB (a CTA pair
 constexpr int kMaxStages = 2 * kKVStages;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
-constexpr int kNumThreads = 384;                    // 2 softmax warpgroups + 1 control warpgroup
+#ifndef FA_EPI_WG
+#define FA_EPI_WG 1           // generation 15: O / l -> 16 bit -> TMA store runs in its own (fourth) warpgroup
+#endif
+constexpr bool kEpiWG = FA_EPI_WG != 0;
+constexpr int kNumThreads = kEpiWG ? 512 : 384;     // 2 softmax warpgroups + control warpgroup (+ epilogue warpgroup)
 constexpr int kTmemCols = 512;
 
 constexpr int kSmemQ = 0;                                       // Q_0, Q_1
 constexpr int kSmemKV = kSmemQ + kQStages * kTileBytes;         // K/V ring
 constexpr int kSmemStage = kSmemKV + kKVStages * kTileBytes;    // O staging: 16 KiB per Q tile
-constexpr int kSmemBar = kSmemStage + kQStages * kHalfBytes;
+constexpr int kSmemL = kSmemStage + kQStages * kHalfBytes;     // float l[2][128]: row sums handed to the epilogue
+constexpr int kSmemBar = kSmemL + kQStages * kBlockM * 4;
 constexpr int kNumBarriers = 4 + 2 * kMaxStages + 13;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBarriers * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16;
@@ -85,15 +90,23 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
 #endif
 #ifndef FA_REGS_SOFTMAX
-#define FA_REGS_SOFTMAX 208   // setmaxnreg for the softmax warpgroups ...
+#define FA_REGS_SOFTMAX (FA_EPI_WG ? 192 : 208)   // setmaxnreg for the softmax warpgroups ...
 #endif
 #ifndef FA_REGS_CTRL
-#define FA_REGS_CTRL 88       // ... and the control warpgroup (2*128*S + 128*C <= 384*168)
+#define FA_REGS_CTRL (FA_EPI_WG ? 64 : 88)        // ... the control warpgroup ...
+#endif
+#ifndef FA_REGS_EPI
+#define FA_REGS_EPI 56                            // ... and the epilogue warpgroup (reads O 32 columns at a time)
+#endif
+#ifndef FA_Q_PREFETCH
+#define FA_Q_PREFETCH 1       // the TMA producer asks for the NEXT work tile's Q rows in L2 while the current tile runs
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
 constexpr bool kSplitP = FA_SPLIT_P != 0;
-static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168, "register pool exceeded");
+static_assert(kEpiWG ? (256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL + 128 * FA_REGS_EPI <= 512 * 128)
+                     : (256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168),
+              "register pool exceeded");
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
@@ -358,6 +371,37 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 if (level >= 3) load_q(1);
                 if (level >= 4) {
                     load_kv(false, 0);
+                    if constexpr (FA_Q_PREFETCH != 0) {
+                        // next work tile of this CTA: its Q rows (2 x 32 KiB) come from HBM exactly once; asking for
+                        // them in L2 now takes the miss latency out of the tile boundary (Q_s is reloaded between the
+                        // last S_s of this tile and the first of the next)
+                        if (tile + n_cta < tile_end && elect_one()) {
+                            const TileCoord nx = coord_of(tile + n_cta);
+#pragma unroll
+                            for (int s = 0; s < kQStages; ++s) {
+                                tma_prefetch_l2_4d(&tm_q, 0, nx.head, nx.q_row0 + s * kBlockM, nx.batch);
+                                tma_prefetch_l2_4d(&tm_q, 64, nx.head, nx.q_row0 + s * kBlockM, nx.batch);
+                            }
+                            if constexpr (FA_Q_PREFETCH >= 2) {
+                                // ... and its first two K / V blocks when it belongs to another (batch, head): the
+                                // first CTA to get there would otherwise take the HBM latency inside the boundary
+                                if (nx.head != tc.head || nx.batch != tc.batch) {
+                                    for (int j = 0; j < 2 && j < n_blocks; ++j) {
+                                        const int krow = j * kBlockN + (kPair ? 64 * (int)rank : 0);
+                                        tma_prefetch_l2_4d(&tm_k, 0, nx.head, krow, nx.batch);
+                                        tma_prefetch_l2_4d(&tm_k, 64, nx.head, krow, nx.batch);
+                                        if constexpr (kPair) {
+                                            tma_prefetch_l2_4d(&tm_v, 64 * (int)rank, nx.head, j * kBlockN, nx.batch);
+                                        } else {
+                                            tma_prefetch_l2_4d(&tm_v, 0, nx.head, j * kBlockN, nx.batch);
+                                            tma_prefetch_l2_4d(&tm_v, 64, nx.head, j * kBlockN, nx.batch);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
                     for (int j = 1; j < n_blocks; ++j) {
                         load_kv(true, j);
                         load_kv(false, j);
@@ -502,7 +546,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             }
         }
         __syncwarp();
-    } else {
+    } else if (wg < 2) {
         // ==================================== softmax =====================================
         setmaxnreg_inc<FA_REGS_SOFTMAX>();
         const int s = wg;                    // Q tile handled by this warpgroup
@@ -616,15 +660,15 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                 wait(pv_done(s), (g - 1u) & 1u, 320 + s);
                         tc_fence_after();
                     
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t o[32];
-                            tmem_ld_32x32b_x32(t_o + q * 32, o);
+#pragma unroll 1
+                        for (int q = 0; q < 8; ++q) {  // 16 columns at a time: S(j) stays in registers
+                            uint32_t o[16];
+                            tmem_ld_32x32b_x16(t_o + q * 16, o);
                             tmem_wait_ld();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
+                            for (int i = 0; i < 16; ++i)
                                 o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st_32x32b_x32(t_o + q * 32, o);
+                            tmem_st_32x32b_x16(t_o + q * 16, o);
                         }
                     }
                 }
@@ -648,7 +692,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                         // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued about one
                     // softmax fragment ago, so this rarely spins)
-                    if (q == 0 && j > 0) {
+                    // (epilogue warpgroup: the first block of a tile overwrites the previous tile's last P_s too;
+                    // without it this warpgroup's own epilogue has waited for that PV)
+                    if (q == 0 && (kEpiWG ? g > 0 : j > 0)) {
                         if constexpr (kDebug) {
                             if (tr) tr[5] = clk32();
                         }
@@ -681,7 +727,20 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
             }
 
             // ------------------------------- epilogue ------------------------------------
-            if (level >= 4) {
+            if constexpr (kEpiWG) {
+                // generation 15: hand the row sum to the epilogue warpgroup and go straight on to the next tile
+                if (level >= 4) {
+                    if constexpr (kDebug) {
+                        if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0) {
+                            dbg.dump[2 * 128 * 128 + s * 128 + row] = l_run;
+                            dbg.dump[2 * 128 * 128 + 256 + s * 128 + row] = m_run;
+                        }
+                    }
+                    if (it > 0) named_bar_sync(12 + s, 256);  // the previous tile's row sum was read
+                    reinterpret_cast<float*>(smem_gen + kSmemL)[s * kBlockM + row] = l_run;
+                    named_bar_arrive(10 + s, 256);
+                }
+            } else if (level >= 4) {
                 wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
                 tc_fence_after();
                 const float inv_l = 1.0f / l_run;
@@ -738,6 +797,72 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 }
             }
         }
+    } else if constexpr (kEpiWG) {
+        // =================================== epilogue (generation 15) =====================================
+        // Own warpgroup (as in the ping-pong kernel): O_s / l -> 16 bit -> swizzled shared memory -> TMA store, for
+        // Q tile 0 then Q tile 1 of every work tile.  With the epilogue inside the softmax warpgroups a tile boundary
+        // cost 1.5-3 us (last PV -> read O -> convert -> store -> only then the next tile's first softmax, with the
+        // tensor pipe idle): ~4 % at seq_len 4096, where a tile is 32 KV blocks (profiles/r02_g15_notes.md).
+        setmaxnreg_dec<FA_REGS_EPI>();
+        const int row = threadIdx.x & 127;
+        const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const float* sm_l = reinterpret_cast<const float*>(smem_gen + kSmemL);
+        uint32_t g_last = 0;  // stream index of the current tile's last KV block (parity of pv_done)
+        int it = 0;
+        for (int tile = cta_lin; level >= 4 && tile < tile_end; tile += n_cta, ++it) {
+            g_last += (uint32_t)n_blocks;
+            const TileCoord tc = coord_of(tile);
+#pragma unroll 1
+            for (int s = 0; s < kQStages; ++s) {
+                named_bar_sync(10 + s, 256);  // softmax warpgroup s has finished the tile: its row sums are written
+                const float inv_l = 1.0f / sm_l[s * kBlockM + row];
+                named_bar_arrive(12 + s, 256);
+                // last PV_s of the tile retired.  No parity aliasing: warpgroup s waited for PV_s(last - 1) before it
+                // stored its last P, and PV_s of the next tile waits for o_free(s) below.
+                wait(pv_done(s), (g_last - 1u) & 1u, 310 + s);
+                tc_fence_after();
+                const uint32_t t_o = tmem_base + lane_sel + tmem_col_o(s);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // 32 columns at a time
+                    const int h = q >> 1;      // TMA box / staging buffer
+                    uint32_t o[32];
+                    tmem_ld_32x32b_x32(t_o + 32 * q, o);
+                    tmem_wait_ld();
+                    if (q == 3) {  // O_s is in registers: the next tile's first PV_s may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_leader(o_free(s));
+                    }
+                    if ((q & 1) == 0) {
+                        // staging buffer h: the store issued two groups ago must have read it (bulk groups of the
+                        // issuing thread complete in order: at most one newer group may still be pending)
+                        if (row == 0) tma_store_wait_read<1>();
+                        named_bar_sync(1, 128);
+                    }
+                    uint8_t* stage_row = smem_gen + kSmemStage + h * kHalfBytes + row * 128;
+#pragma unroll
+                    for (int cidx = 0; cidx < 4; ++cidx) {
+                        uint4 v;
+                        v.x = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 0]) * inv_l, __uint_as_float(o[cidx * 8 + 1]) * inv_l);
+                        v.y = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 2]) * inv_l, __uint_as_float(o[cidx * 8 + 3]) * inv_l);
+                        v.z = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 4]) * inv_l, __uint_as_float(o[cidx * 8 + 5]) * inv_l);
+                        v.w = pack_16x2<kBF16>(__uint_as_float(o[cidx * 8 + 6]) * inv_l, __uint_as_float(o[cidx * 8 + 7]) * inv_l);
+                        const int chunk = ((q & 1) * 4 + cidx) ^ (row & 7);  // TMA 128B swizzle
+                        *reinterpret_cast<uint4*>(stage_row + chunk * 16) = v;
+                    }
+                    if (q & 1) {
+                        fence_proxy_async_smem();
+                        named_bar_sync(1, 128);
+                        if (row == 0) {
+                            tma_store_4d(&tm_o, smem_base + kSmemStage + h * kHalfBytes, 64 * h, tc.head,
+                                         tc.q_row0 + s * kBlockM, tc.batch);
+                            tma_store_commit();
+                        }
+                    }
+                }
+            }
+        }
+        if (row == 0) tma_store_wait_read<0>();  // shared memory must outlive the last store's read
     }
 
     // ------------------------------------ teardown ---------------------------------------

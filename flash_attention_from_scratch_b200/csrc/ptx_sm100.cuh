@@ -189,6 +189,12 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst_smem, const CUtens
         ::"r"(dst_smem), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
+// 4-D tiled prefetch global -> L2 only (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // 4-D tiled store shared -> global (bulk-group completion).
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0,
                                              int c1, int c2, int c3) {

@@ -35,6 +35,9 @@ VARIANTS = {
     "ppexpv1": {"FA_EXP_VARIANT": 1},
     "hint": {"FA_WAIT_HINT": 10000000},   # CUTLASS-style 10 ms suspend-time hint on every try_wait
     "sleep32": {"FA_WAIT_SLEEP": 32},     # nanosleep back-off in the wait loops
+    "noepi": {"FA_EPI_WG": 0},            # generation 14: epilogue inside the softmax warpgroups (384 threads)
+    "kvpf": {"FA_Q_PREFETCH": 2},         # ... plus the next tile's first two K/V blocks when (batch, head) changes
+    "noqpf": {"FA_Q_PREFETCH": 0},        # generation 15 without the L2 prefetch of the next tile's Q
 }
 
 
