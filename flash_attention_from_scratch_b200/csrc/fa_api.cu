@@ -86,15 +86,16 @@ cudaError_t set_smem_attr() {
 }
 
 // Kernel choice (include/fa_sm100.h: fa_set_kernel_mode).  Measured on one B200 with the reference's benchmark
-// shapes (profiles/r02_sweep_g14.json, TFLOP/s, mean of 12, L2 flushed):
-//   seq_len      512   1024   2048   4096(H=32)   8192   16384
-//   ping-pong    846   1278   1442      1464       1474    1374
-//   CTA pairs    711   1198   1431      1483       1512    1460
-//   single CTAs  738   1210   1399      1441       1439    1357
-// The ping-pong kernel has twice as many (half as large) work tiles and no serial chain through a shared S
-// accumulator, which wins while tiles are short; the pair kernel moves half the K/V bytes per FLOP and runs its
-// epilogue half as often, which wins from 4096 on.
-constexpr int kPingPongMaxSeqLen = 2048;  // AUTO: ping-pong kernel up to this, CTA pairs above
+// shapes (profiles/r02_g15_sweep_modes.json, generation 15, TFLOP/s, mean of 12, L2 flushed; that box runs ~4 %
+// below the one of profiles/r02_g15_sweep.json):
+//   seq_len      512   1024   2048   4096   8192   16384   4096 (H=32)
+//   ping-pong    820   1242   1365   1358   1322    1303      1380
+//   CTA pairs    704   1237   1428   1435   1415    1366      1456
+//   single CTAs  730   1238   1392   1392   1357    1315      1387
+// The ping-pong kernel has twice as many (half as large) work tiles, which wins while tiles are short; the pair
+// kernel moves half the K/V bytes per FLOP.  Since generation 15 (epilogue warpgroup: no bubble at the tile
+// boundary any more) the pair kernel wins from 2048 on (generation 14: from 4096 on).
+constexpr int kPingPongMaxSeqLen = 1024;  // AUTO: ping-pong kernel up to this, CTA pairs above
 std::atomic<int> g_mode{[] {
     const char* m = getenv("FA_SM100_MODE");
     if (m != nullptr && strcmp(m, "single") == 0) return FA_MODE_SINGLE;

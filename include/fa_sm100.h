@@ -85,7 +85,7 @@ int64_t fa_launch_count(void);
 /* Which kernel a launch uses.  The reference selects one of its 85 template instantiations with the
  * kernel_cfg map lookup (flash_attention.cu:59-62); this library has two machine mappings of the same
  * arithmetic (three kernels) and picks by shape:
- *   FA_MODE_AUTO     (default): the ping-pong kernel up to seq_len 2048, CTA pairs above (measured crossover)
+ *   FA_MODE_AUTO     (default): the ping-pong kernel up to seq_len 1024, CTA pairs above (measured crossover)
  *   FA_MODE_SINGLE   one CTA per SM, work tile = 256 query rows
  *   FA_MODE_PAIR     clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
  *   FA_MODE_PINGPONG clusters of two CTAs, one 128-row Q tile per CTA, two S accumulators (tile = 256 rows)

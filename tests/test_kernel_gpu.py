@@ -104,7 +104,7 @@ def test_matches_sdpa(dtype, B, N, H):
                                          (torch.bfloat16, 5, 384, 33), (torch.float16, 9, 128, 41),
                                          (torch.bfloat16, 1, 2304, 3), (torch.float16, 1, 4096, 2)])
 def test_every_machine_mapping(mode, dtype, B, N, H):
-    """AUTO picks the ping-pong kernel up to seq_len 2048 and CTA pairs above; all three kernels must give the
+    """AUTO picks the ping-pong kernel up to seq_len 1024 and CTA pairs above; all three kernels must give the
     same answer at every shape, including pairs whose second CTA has no valid query rows."""
     q, k, v = rand_qkv((B, N, H, 128), dtype, seed=N + H)
     with kernel_mode(mode):

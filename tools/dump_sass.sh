@@ -6,8 +6,8 @@ cd "$(dirname "$0")/.."
 LIB=flash_attention_from_scratch_b200/csrc/libfa_sm100.so
 TAG=${1:-r01}
 # production instantiations: bf16, no debug hooks, seq_len % 128 == 0
-#   fa_fwd_kernel_pair<true,false,false>  (CTA pairs, AUTO for seq_len > 2048)      -> *_pair_bf16.sass
-#   pp::fa_fwd_kernel_pp<true,false,false> (ping-pong, AUTO for seq_len <= 2048)   -> *_pp_bf16.sass
+#   fa_fwd_kernel_pair<true,false,false>  (CTA pairs, AUTO for seq_len > 1024)      -> *_pair_bf16.sass
+#   pp::fa_fwd_kernel_pp<true,false,false> (ping-pong, AUTO for seq_len <= 1024)   -> *_pp_bf16.sass
 #   fa_fwd_kernel<true,false,false>       (single CTA, explicit mode only)         -> *_bf16.sass
 cuobjdump -sass "$LIB" | awk '/Function :/{on = ($0 ~ /fa_fwd_kernel_pairILb1ELb0ELb0E/)} on' > profiles/${TAG}_fa_fwd_kernel_pair_bf16.sass
 cuobjdump -sass "$LIB" | awk '/Function :/{on = ($0 ~ /fa_fwd_kernelILb1ELb0ELb0E/)} on' > profiles/${TAG}_fa_fwd_kernel_bf16.sass
