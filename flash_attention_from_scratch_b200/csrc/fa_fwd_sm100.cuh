@@ -98,6 +98,9 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #ifndef FA_REGS_EPI
 #define FA_REGS_EPI 56                            // ... and the epilogue warpgroup (reads O 32 columns at a time)
 #endif
+#ifndef FA_TRACE
+#define FA_TRACE 0            // 1: the production instantiations can record the cycle trace too (development builds)
+#endif
 #ifndef FA_Q_PREFETCH
 #define FA_Q_PREFETCH 1       // the TMA producer asks for the NEXT work tile's Q rows in L2 while the current tile runs
 #endif
@@ -152,6 +155,7 @@ struct FwdDebug {
 };
 
 constexpr int kTraceBase = 2 * 128 * 128 + 512;  // word offset of the trace inside FwdDebug::dump
+constexpr int kTraceTile = 1;                    // the CTA's work tile the cycle trace records (steady state)
 __device__ __forceinline__ uint32_t clk32() {
     uint32_t c;
     asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
@@ -239,6 +243,10 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
 
     const int n_blocks = prm.n_kv_blocks;
     const uint32_t level = kDebug ? dbg.level : 4u;
+    // cycle trace (tools/gpu_trace2.py): the debug instantiation at level >= 5, or -- in -DFA_TRACE=1 builds -- the
+    // production instantiation whenever a dump buffer is passed (fa_fwd_debug with level 40)
+    constexpr bool kTr = kDebug || (FA_TRACE != 0);
+    const bool tracing = kTr && (kDebug ? level >= 5 : true) && dbg.dump != nullptr && blockIdx.x == 0;
     // work tiles of this CTA (pair): cta_lin, cta_lin + n_cta, ...  (q-group index fastest so the
     // CTAs running at the same time share the K/V of a few (batch, head) pairs in L2)
     const int tile_end = (kDebug && level < 4) ? min(prm.n_tiles, cta_lin + 1) : prm.n_tiles;
@@ -471,8 +479,17 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         wait(kv_full(slot), (uint32_t)((kb / kH) & 1), 200);
 #pragma unroll
                         for (int s = 0; s < kQStages; ++s) {
+                            uint32_t* tr = nullptr;
+                            if constexpr (kTr) {
+                                if (tracing && it == kTraceTile && jj < 32 && lane == 0)
+                                    tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 768 + (jj * 2 + s) * 4;
+                                if (tr) tr[0] = clk32();
+                            }
                             if (jj == 0) wait(q_full(s), (uint32_t)(it & 1), 210 + s);
                             if (u > 0) wait(s_free, (u - 1u) & 1u, 270 + s);
+                            if constexpr (kTr) {
+                                if (tr) tr[1] = clk32();
+                            }
                             tc_fence_after();
                             if (elect_one()) {
                                 issue_qk_b(s, kd);
@@ -481,6 +498,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                 if (s == 1) commit(kv_empty(slot));          // both tiles used K_jj
                             }
                             __syncwarp();
+                            if constexpr (kTr) {
+                                if (tr) tr[2] = clk32();
+                            }
                             ++u;
                         }
                     }
@@ -504,6 +524,12 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     wait(kv_full(slot), (uint32_t)((vb / kH) & 1), 220);
 #pragma unroll
                     for (int s = 0; s < kQStages; ++s) {
+                        uint32_t* tr = nullptr;
+                        if constexpr (kTr) {
+                            if (tracing && it == kTraceTile && j < 32 && lane == 0)
+                                tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + 512 + (j * 2 + s) * 4;
+                            if (tr) tr[0] = clk32();
+                        }
                         wait(p_full(s), par, 230 + s);  // P_s(j) stored (first 96 keys), O_s rescaled
                         if (j == 0)  // previous tile's epilogue has read O_s out of TMEM
                             wait(o_free(s), (uint32_t)((it & 1) ^ 1), 260 + s);
@@ -528,11 +554,17 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                                             vd + ((k * 2048) >> 4), idesc_pv, acc);
                             }
                         };
+                        if constexpr (kTr) {
+                            if (tr) tr[1] = clk32();
+                        }
                         if (elect_one()) pv(0, kSplitP ? 6 : 8);
                         __syncwarp();
                         if constexpr (kSplitP) {
                             wait(p_last(s), par, 250 + s);  // last 32 keys of P_s(j)
                             tc_fence_after();
+                        }
+                        if constexpr (kTr) {
+                            if (tr) tr[2] = clk32();
                         }
                         if (elect_one()) {
                             if constexpr (kSplitP) pv(6, 8);
@@ -540,6 +572,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                             if (s == 1) commit(kv_empty(slot));
                         }
                         __syncwarp();
+                        if constexpr (kTr) {
+                            if (tr) tr[3] = clk32();
+                        }
                     }
                 }
                 g0 += (uint32_t)n_blocks;
@@ -579,9 +614,8 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 wait(s_full(s), g & 1u, 300 + s);
                 tc_fence_after();
                 uint32_t* tr = nullptr;
-                if constexpr (kDebug) {
-                    if (level >= 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j < 32 &&
-                        (warp & 3) == 0 && lane == 0)
+                if constexpr (kTr) {
+                    if (tracing && it == kTraceTile && j < 32 && (warp & 3) == 0 && lane == 0)
                         tr = reinterpret_cast<uint32_t*>(dbg.dump) + kTraceBase + (s * 32 + j) * 8;
                     if (tr) tr[0] = clk32();
                 }
@@ -618,7 +652,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     if (lane == 0) arrive_leader(s_free);
                 }
                 
-                if constexpr (kDebug) {
+                if constexpr (kTr) {
                     if (tr) tr[1] = clk32();
                 }
                 if (kRagged && j + 1 == n_blocks && kv_tail != 0) {
@@ -626,7 +660,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 }
 
                 if constexpr (kDebug) {
-                    if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j == 0) {
+                    if (level < 5 && dbg.dump != nullptr && blockIdx.x == 0 && it == 0 && j == 0) {
                         for (int q = 0; q < 4; ++q)
                             for (int i = 0; i < 32; ++i)
                                 dbg.dump[(s * 128 + row) * 128 + q * 32 + i] =
@@ -672,7 +706,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         }
                     }
                 }
-                if constexpr (kDebug) {
+                if constexpr (kTr) {
                     if (tr) tr[2] = clk32();
                 }
                 const float neg_mc = -m_run * c;
@@ -695,12 +729,12 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     // (epilogue warpgroup: the first block of a tile overwrites the previous tile's last P_s too;
                     // without it this warpgroup's own epilogue has waited for that PV)
                     if (q == 0 && (kEpiWG ? g > 0 : j > 0)) {
-                        if constexpr (kDebug) {
+                        if constexpr (kTr) {
                             if (tr) tr[5] = clk32();
                         }
                         wait(pv_done(s), (g - 1u) & 1u, 330 + s);
                         tc_fence_after();
-                        if constexpr (kDebug) {
+                        if constexpr (kTr) {
                             if (tr) tr[6] = clk32();
                         }
                     }
@@ -711,7 +745,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) arrive_leader(p_full(s));
-                        if constexpr (kDebug) {
+                        if constexpr (kTr) {
                             if (tr) tr[3] = clk32();
                         }
                     }
@@ -720,7 +754,7 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_leader(kSplitP ? p_last(s) : p_full(s));
-                if constexpr (kDebug) {
+                if constexpr (kTr) {
                     if (tr) tr[4] = clk32();
                 }
                 l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));

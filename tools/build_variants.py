@@ -38,6 +38,7 @@ VARIANTS = {
     "noepi": {"FA_EPI_WG": 0},            # generation 14: epilogue inside the softmax warpgroups (384 threads)
     "kvpf": {"FA_Q_PREFETCH": 2},         # ... plus the next tile's first two K/V blocks when (batch, head) changes
     "r200": {"FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 56, "FA_REGS_EPI": 56},
+    "trace": {"FA_TRACE": 1},             # production instantiations record the cycle trace (tools/gpu_trace2.py)
     "noqpf": {"FA_Q_PREFETCH": 0},        # generation 15 without the L2 prefetch of the next tile's Q
 }
 
