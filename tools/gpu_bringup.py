@@ -69,7 +69,7 @@ def run_one(args):
     q_img = swizzled_image(q[0, :128, 0].cpu())
     # CTA pairs (seq_len > 1024 unless FA_SM100_MODE says otherwise): CTA 0 holds keys 0..63 of K_0
     mode = os.environ.get("FA_SM100_MODE", "auto")
-    pair = mode == "pair" or (mode != "single" and N > 1024)
+    pair = mode != "single"  # AUTO and the explicit cluster modes all use CTA pairs (K split in 64-key halves)
     k_img = swizzled_image(k[0, :(64 if pair else 128), 0].cpu())
     ref = None
     if level >= 4:
