@@ -3,7 +3,7 @@
 # the 2-device GPU test.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r02
+T=r02_final
 nvidia-smi -L | wc -l
 timeout 300 python -m pytest tests -m gpu -x -q --timeout 200 -k "second_device or concurrent" 2>&1 | tail -2
 for N in 8 4 2 1; do
@@ -16,7 +16,7 @@ try:
 except Exception as e: print('shard16k N=$N failed', e)
 PY
 done
-for N in 8 4 2; do
+for N in 8 4 2 1; do
   timeout 400 python bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-sustained > gpurun_out/${T}_bench_n${N}_weak.json 2> gpurun_out/${T}_bench_n${N}_weak.err
   python - <<PY
 import json
