@@ -429,6 +429,15 @@ def main():
     else:
         kern_ms = local_flops / (sweep_rows[3]["kernel_tflops"] * 1e12) * 1e3
         region_ms = None
+    # host cost of one call through the Python operator (argument checks, cached TMA descriptors, launch):
+    # asynchronous calls, wall clock / calls -- the launch queue never fills, so this is pure host time
+    torch.cuda.synchronize()
+    n_host = 200 if kern_ms < 1.0 else 20  # (long kernels: keep the queued GPU time well under a second)
+    t_h0 = time.perf_counter()
+    for i in range(n_host):
+        fa.forward(None, *sets[i % len(sets)])
+    host_us = (time.perf_counter() - t_h0) / n_host * 1e6
+    torch.cuda.synchronize()
     sustained_rec = None
     if not args.no_sustained:
         sustained_rec = measure_sustained(sets, global_flops)
@@ -510,6 +519,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "host_us_per_call": host_us,
+            "tensor_map_cache": _lib.tensor_map_cache_stats(),
         }
         if back_to_back is not None:
             line["back_to_back"] = back_to_back
