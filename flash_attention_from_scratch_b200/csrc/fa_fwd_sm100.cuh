@@ -645,7 +645,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     // ptxas hoists the arrive (and with it the stall on the last tcgen05.ld) above the reduction of
                     // the first half; a never-true dependency on m_lo keeps it behind.  Never true: m_lo comes out
                     // of an FMNMX chain, whose only NaN result is the canonical 0x7fffffff (one input NaN -> the
-                    // other input; both NaN -> canonical NaN), never this payload.
+                    // other input; both NaN -> canonical NaN), never this payload.  (A form that is correct for ANY
+                    // m_lo -- two equivalent predicated arrives chosen by the same comparison -- was measured: -2.5 %
+                    // pair, -8 % single, profiles/r02_g15_arrive_form_sweep.json; comments only, SASS unchanged.)
                     const uint32_t skew = (__float_as_uint(m_lo) == 0x7fc12345u) ? 8u : 0u;
                     if (lane == 0) arrive_leader(s_free + skew);
                 } else {
