@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Deadlock check of the ping-pong kernel's barrier protocol (csrc/fa_fwd_pp_sm100.cuh) on the CPU.
+"""Deadlock check of the kernels' barrier protocols on the CPU: `simulate` = the ping-pong kernel
+(csrc/fa_fwd_pp_sm100.cuh), `simulate_shared_s` = the CTA-pair / single-CTA kernels (csrc/fa_fwd_sm100.cuh).
 
 Every agent of one CTA pair (the two TMA producers, the two MMA-issuing warps, the two softmax warpgroups, the
 epilogue warpgroup) is a generator that yields
@@ -123,11 +124,158 @@ def simulate(n, tiles, k_stages=4, v_stages=4, verbose=False):
     return True
 
 
+def simulate_shared_s(n, tiles, ring=4, rescale=False, epi_wg=True, verbose=False, lazy=None):
+    """The shared-S kernels of csrc/fa_fwd_sm100.cuh (generation 15: CTA pairs and single CTAs): one TMA producer,
+    the S-issuing warp, the PV-issuing warp, two softmax warpgroups (one per Q tile) and the epilogue warpgroup.
+    `ring` = K (and V) ring slots; `rescale` = every block takes the lazy-rescale path (it waits for the previous PV
+    of its tile: data dependent in the kernel, so both extremes are checked); `epi_wg=False` = generation 14 (the
+    softmax warpgroups run their own epilogue).  Besides deadlocks it checks the PARITY discipline: a wait that
+    finds its barrier more than one completion ahead would, with the kernel's parity waits, block for ever -- the
+    scheduler lets every agent run as far ahead as the protocol allows, so such a barrier shows up here.
+    `lazy` names an agent that only moves when nobody else can (the adversarial schedule for that agent's waits).
+    Returns True when every agent finishes and no barrier ever ran ahead of a waiter."""
+    done = {}
+    ahead = []
+
+    def cnt(name):
+        return done.get(name, 0)
+
+    def sig(name):
+        done[name] = cnt(name) + 1
+
+    def producer():
+        x_k = x_v = 0  # K / V blocks loaded so far (all tiles): ring slot and use count
+
+        def load(kind, x):
+            slot, use = x % ring, x // ring
+            if use > 0:
+                yield ("%s_empty%d" % (kind, slot), use)
+            sig("%s_full%d" % (kind, slot))
+
+        for it in range(tiles):
+            if it > 0:
+                yield ("q_empty0", it)
+            sig("q_full0")
+            yield from load("k", x_k); x_k += 1
+            if it > 0:
+                yield ("q_empty1", it)
+            sig("q_full1")
+            yield from load("v", x_v); x_v += 1
+            for _ in range(1, n):
+                yield from load("k", x_k); x_k += 1
+                yield from load("v", x_v); x_v += 1
+
+    def mma_s():
+        kb = u = 0
+        for it in range(tiles):
+            for jj in range(n):
+                yield ("k_full%d" % (kb % ring), kb // ring + 1)
+                for s in (0, 1):
+                    if jj == 0:
+                        yield ("q_full%d" % s, it + 1)
+                    if u > 0:
+                        yield ("s_free", u)          # the previous S (either tile) was read out
+                    sig("s_full%d" % s)
+                    if jj == n - 1:
+                        sig("q_empty%d" % s)
+                    if s == 1:
+                        sig("k_empty%d" % (kb % ring))
+                    u += 1
+                kb += 1
+
+    def mma_pv():
+        vb = 0
+        for it in range(tiles):
+            for j in range(n):
+                g = it * n + j
+                yield ("v_full%d" % (vb % ring), vb // ring + 1)
+                for s in (0, 1):
+                    yield ("p_full%d" % s, g + 1)
+                    if j == 0 and it > 0:
+                        yield ("o_free%d" % s, it)   # the previous tile's O_s was read out
+                    yield ("p_last%d" % s, g + 1)
+                    sig("pv_done%d" % s)
+                    if s == 1:
+                        sig("v_empty%d" % (vb % ring))
+                vb += 1
+
+    def softmax(s):
+        for it in range(tiles):
+            for j in range(n):
+                g = it * n + j
+                yield ("s_full%d" % s, g + 1)
+                sig("s_free")
+                if rescale and j > 0:
+                    yield ("pv_done%d" % s, g)       # O_s quiescent before it is rescaled
+                if (g > 0) if epi_wg else (j > 0):
+                    yield ("pv_done%d" % s, g)       # P_s(g-1) consumed before P_s(g) overwrites it
+                sig("p_full%d" % s)
+                sig("p_last%d" % s)
+            if epi_wg:
+                if it > 0:
+                    yield ("l_free%d" % s, it)       # named barrier 12 + s
+                sig("l_ready%d" % s)                 # named barrier 10 + s
+            else:
+                yield ("pv_done%d" % s, (it + 1) * n)
+                sig("o_free%d" % s)
+
+    def epilogue():
+        for it in range(tiles):
+            for s in (0, 1):
+                yield ("l_ready%d" % s, it + 1)
+                sig("l_free%d" % s)
+                yield ("pv_done%d" % s, (it + 1) * n)
+                sig("o_free%d" % s)
+
+    agents = {"producer": producer(), "mma_s": mma_s(), "mma_pv": mma_pv(), "wg0": softmax(0), "wg1": softmax(1)}
+    if epi_wg:
+        agents["epilogue"] = epilogue()
+    waiting = {}
+    for name, gen in list(agents.items()):
+        try:
+            waiting[name] = next(gen)
+        except StopIteration:
+            del agents[name]
+    def step(name, once=False):
+        moved = False
+        while name in agents and cnt(waiting[name][0]) >= waiting[name][1]:
+            bar, need = waiting[name]
+            if cnt(bar) > need:  # the barrier ran ahead of this waiter: a parity wait could miss the phase
+                ahead.append((name, bar, need, cnt(bar)))
+            moved = True
+            try:
+                waiting[name] = next(agents[name])
+            except StopIteration:
+                del agents[name]
+            if once:
+                break
+        return moved
+
+    progress = True
+    while agents and progress:
+        progress = False
+        for name in list(agents):
+            if name != lazy and step(name):
+                progress = True
+        if not progress and lazy in agents:
+            progress = step(lazy, once=True)  # one wait at a time, then everybody else runs ahead again
+    if agents or ahead:
+        if verbose:
+            print("FAIL n=%d tiles=%d ring=%d:" % (n, tiles, ring),
+                  {a: (waiting[a], cnt(waiting[a][0])) for a in agents}, ahead[:4])
+        return False
+    return True
+
+
 def main():
     bad = 0
     for n, tiles, ks, vs in itertools.product(range(1, 9), range(1, 6), (2, 4), (2, 4)):
         if not simulate(n, tiles, ks, vs, verbose=True):
             bad += 1
+    for n, tiles, ring, rescale, epi in itertools.product(range(1, 9), range(1, 6), (2, 4), (False, True), (True, False)):
+        for lazy in (None, "producer", "mma_s", "mma_pv", "wg0", "wg1", "epilogue"):
+            if not simulate_shared_s(n, tiles, ring, rescale, epi, verbose=True, lazy=lazy):
+                bad += 1
     print("deadlocks:", bad)
     return 1 if bad else 0
 
