@@ -27,6 +27,9 @@ CASES = [
     ("bf16_2x256x3", 1, torch.bfloat16, (2, 256, 3, 128)),
     ("fp16_2x256x3", 2, torch.float16, (2, 256, 3, 128)),
     ("bf16_1x512x1", 3, torch.bfloat16, (1, 512, 1, 128)),
+    # long enough for AUTO to pick the CTA-pair kernel (seq_len > 1024): 10 KV blocks, 3 work tiles of 512 rows,
+    # the last one half empty
+    ("bf16_1x1280x1", 4, torch.bfloat16, (1, 1280, 1, 128)),
 ]
 
 

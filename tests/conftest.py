@@ -22,7 +22,7 @@ def lib():
 
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["cfg1_bf16_1x128x2", "bf16_2x256x3", "fp16_2x256x3", "bf16_1x512x1"]
+GOLDEN_CASES = ["cfg1_bf16_1x128x2", "bf16_2x256x3", "fp16_2x256x3", "bf16_1x512x1", "bf16_1x1280x1"]
 
 
 @pytest.fixture(scope="session", params=GOLDEN_CASES)

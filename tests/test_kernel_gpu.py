@@ -61,8 +61,8 @@ class kernel_mode:
 # ------------------------------------------------------------------ golden fixtures (reference-made)
 @pytest.mark.parametrize("mode", ["auto"] + MODES)
 def test_golden_fixtures(golden, mode):
-    """The fixtures made by the reference's own Python functions, through every kernel of the library (AUTO alone
-    would only ever run the ping-pong kernel on them: they stop at seq_len 512)."""
+    """The fixtures made by the reference's own Python functions, through every kernel of the library (AUTO sends the
+    fixtures up to seq_len 512 to the ping-pong kernel and bf16_1x1280x1 to the CTA-pair kernel)."""
     q, k, v = (golden[n].to(DEV) for n in "qkv")
     with kernel_mode(mode):
         out = flash_attention.forward(cfg_for(q.dtype), q, k, v).cpu()
