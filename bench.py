@@ -109,7 +109,7 @@ def load_ncu_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML)."""
 
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.001):
         super().__init__(daemon=True)
         self.index = index
         self.period = period
@@ -141,10 +141,15 @@ class ClockSampler(threading.Thread):
             nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
         }
+        n = 0
         while not self.stop_flag.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.power_mw.append(nv.nvmlDeviceGetPowerUsage(self.h))
+                # an NVML call costs about a millisecond and the power reading is a ~1 s average anyway: in the fast
+                # sampler (short timed regions) read it every fourth time only
+                if self.period >= 0.005 or n % 4 == 0:
+                    self.power_mw.append(nv.nvmlDeviceGetPowerUsage(self.h))
+                n += 1
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if mask & bit:
@@ -262,6 +267,9 @@ def main():
     if "WORLD_SIZE" not in os.environ and args.gpus > 1:
         respawn_under_torchrun(args.gpus)  # (before stdout is claimed: the ranks inherit the descriptors)
     claim_stdout()
+    # the NVML sampler thread must get the interpreter often enough to see a 15 ms timed region more than once
+    # (default switch interval: 5 ms)
+    sys.setswitchinterval(2e-4)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
