@@ -30,6 +30,7 @@ SYMBOLS = {
     "fa_kernel_info": (_I, [C.POINTER(_I)] * 4),
     "fa_launch_count": (_L, []),
     "fa_last_kernel": (_I, []),
+    "fa_pick_kernel": (_I, [_I, _I, _I, _I]),
     "fa_tensor_map_cache_stats": (_I, [C.POINTER(_L), C.POINTER(_L)]),
     "fa_set_kernel_mode": (_I, [_I]),
     "fa_set_thread_kernel_mode": (_I, [_I]),
@@ -76,6 +77,12 @@ KERNEL_NAMES = {MODE_SINGLE: "fa_fwd_kernel", MODE_PAIR: "fa_fwd_kernel_pair", M
 def last_kernel() -> str:
     """Name of the kernel the calling thread's last launch used (what AUTO picked)."""
     return KERNEL_NAMES.get(int(load().fa_last_kernel()), "none")
+
+
+def pick_kernel(seq_len: int, batch: int, n_heads: int, n_sms: int = 0) -> str:
+    """The kernel the library would launch for this problem (no launch): the C side's AUTO rule."""
+    return {1: "fa_fwd_kernel", 2: "fa_fwd_kernel_pair", 3: "fa_fwd_kernel_pp"}.get(
+        int(load().fa_pick_kernel(seq_len, batch, n_heads, n_sms)), "?")
 
 
 def tensor_map_cache_stats() -> dict:

@@ -107,10 +107,17 @@ thread_local int t_mode = -1;  // fa_set_thread_kernel_mode: per-thread override
 int pick_kernel(int seq_len, int batch, int n_heads, int n_sms) {  // FA_MODE_SINGLE, _PAIR or _PINGPONG
     const int mode = t_mode >= 0 ? t_mode : g_mode.load(std::memory_order_relaxed);
     if (mode != FA_MODE_AUTO) return mode;
-    (void)batch;
-    (void)n_heads;
-    (void)n_sms;
-    return seq_len > kPingPongMaxSeqLen ? FA_MODE_PAIR : FA_MODE_PINGPONG;
+    if (seq_len <= kPingPongMaxSeqLen) return FA_MODE_PINGPONG;
+    // Above the crossover the pair kernel is ~5 % faster per unit of work, but its work tile is twice as large (512
+    // rows per CTA pair against 256): on grids of a few waves the ping-pong kernel can need fewer (half-size) waves
+    // -- (1, 2048, 4): 16 tiles on 74 pairs = one wave of 2 units against 32 half tiles = one wave of 1 unit.
+    // Cost model in units of "one 256-row tile": waves x tile size (x 1.05 for the ping-pong kernel).
+    const long long pairs = n_sms / 2 > 0 ? n_sms / 2 : 1;
+    const long long heads = (long long)batch * n_heads;
+    const long long t_pair = heads * ((seq_len + 511) / 512), t_pp = heads * ((seq_len + 255) / 256);
+    const double cost_pair = 2.0 * (double)((t_pair + pairs - 1) / pairs);
+    const double cost_pp = 1.05 * (double)((t_pp + pairs - 1) / pairs);
+    return cost_pp < cost_pair ? FA_MODE_PINGPONG : FA_MODE_PAIR;
 }
 
 // One-time per-device setup: capability check + opt-in dynamic shared memory
@@ -385,6 +392,10 @@ int64_t fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed
 
 int fa_last_kernel(void) { return t_last_kernel; }
 
+int fa_pick_kernel(int seq_len, int batch, int n_heads, int n_sms) {
+    return pick_kernel(seq_len, batch, n_heads, n_sms > 0 ? n_sms : 148);
+}
+
 int fa_tensor_map_cache_stats(int64_t* hits, int64_t* misses) {
     if (hits) *hits = g_map_hits.load(std::memory_order_relaxed);
     if (misses) *misses = g_map_misses.load(std::memory_order_relaxed);
@@ -543,6 +554,10 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
         FA_CUDA(cudaGetDevice(&cur));
         if (cur != device) return fail(FA_ERR_DEVICE, "cudaSetDevice(%d) failed", device);
     }
+    {
+        const int irc = init_device(device);  // capability check; the SM count feeds the kernel choice below
+        if (irc != FA_OK) return irc;
+    }
     HostWorkspace& w = g_ws[device];
     // the workspace and its three streams are per device: calls for one device are serialised, calls for
     // different devices (one per rank / thread) run concurrently
@@ -578,6 +593,13 @@ int fa_fwd_host(const void* q_host, const void* k_host, const void* v_host, void
         if (rc == FA_OK && e != cudaSuccess) rc = fail(FA_ERR_LAUNCH, "%s failed: %s", what, cudaGetErrorString(e));
         return rc == FA_OK;
     };
+    // The kernel is chosen ONCE, for the whole problem, and forced for the per-batch-entry launches: AUTO looks at
+    // the grid, and the answer must not depend on how this entry chunks the work (the device entry sees one launch).
+    struct ModeGuard {
+        int prev;
+        explicit ModeGuard(int m) : prev(t_mode) { t_mode = m; }
+        ~ModeGuard() { t_mode = prev; }
+    } mode_guard(pick_kernel(seq_len, batch, n_heads, g_dev[device].n_sms > 0 ? g_dev[device].n_sms : 148));
     for (int b = 0; b < batch && rc == FA_OK; ++b) {
         const size_t off = per_batch * b;
         const void* src[3] = {q_host, k_host, v_host};

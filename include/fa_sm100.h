@@ -85,7 +85,8 @@ int64_t fa_launch_count(void);
 /* Which kernel a launch uses.  The reference selects one of its 85 template instantiations with the
  * kernel_cfg map lookup (flash_attention.cu:59-62); this library has two machine mappings of the same
  * arithmetic (three kernels) and picks by shape:
- *   FA_MODE_AUTO     (default): the ping-pong kernel up to seq_len 1024, CTA pairs above (measured crossover)
+ *   FA_MODE_AUTO     (default): the ping-pong kernel up to seq_len 1024, CTA pairs above (measured crossover) except on grids of
+ *                    a few waves where half-size tiles need fewer of them (fa_pick_kernel)
  *   FA_MODE_SINGLE   one CTA per SM, work tile = 256 query rows
  *   FA_MODE_PAIR     clusters of two CTAs sharing every K/V block (tcgen05 cta_group::2), tile = 512 rows
  *   FA_MODE_PINGPONG clusters of two CTAs, one 128-row Q tile per CTA, two S accumulators (tile = 256 rows)
@@ -107,6 +108,12 @@ int fa_set_thread_kernel_mode(int mode);
 /* FA_MODE_SINGLE / FA_MODE_PAIR / FA_MODE_PINGPONG of the calling thread's last launch (-1: none yet): what
  * AUTO actually picked, so that callers (bench.py) need not re-implement the rule. */
 int fa_last_kernel(void);
+
+/* The kernel AUTO (or the mode in force for the calling thread) would launch for this problem on a device with
+ * `n_sms` SMs (<= 0: 148), without launching anything: FA_MODE_SINGLE / FA_MODE_PAIR / FA_MODE_PINGPONG.  AUTO =
+ * ping-pong up to seq_len 1024; above, CTA pairs unless the grid is so small that the ping-pong kernel's half-size
+ * work tiles need fewer waves (cost model in csrc/fa_api.cu: pick_kernel). */
+int fa_pick_kernel(int seq_len, int batch, int n_heads, int n_sms);
 
 /* Hit / miss counters of the per-thread cache of encoded TMA tensor maps (key: pointer, shape, strides, dtype;
  * the reference builds nothing per call, its kernel takes raw pointers: flash_attention.cu:107-110). */

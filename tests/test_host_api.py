@@ -174,3 +174,24 @@ def test_forward_host_rejects_a_bad_output_buffer():
             op.forward_host(q, q, q, bad)
     with pytest.raises(RuntimeError, match="was not found"):
         op.forward_host(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())
+
+
+def test_auto_kernel_choice_is_grid_aware(lib):
+    """AUTO (csrc/fa_api.cu: pick_kernel) without a GPU: ping-pong up to seq_len 1024, CTA pairs above -- except where
+    the pair kernel's 512-row work tiles leave the machine under-filled and half-size tiles need fewer waves."""
+    from flash_attention_from_scratch_b200 import _lib
+
+    pk = lambda B, N, H: _lib.pick_kernel(N, B, H, 148)  # noqa: E731
+    # BASELINE's shapes: the reference's sweep, the headline, the 8-way shard of config 5
+    assert [pk(16, n, 16) for n in (512, 1024)] == ["fa_fwd_kernel_pp"] * 2
+    assert [pk(b, n, 16) for b, n in ((16, 2048), (16, 4096), (8, 8192), (4, 16384))] == ["fa_fwd_kernel_pair"] * 4
+    assert pk(4, 4096, 32) == "fa_fwd_kernel_pair" and pk(1, 16384, 32) == "fa_fwd_kernel_pair"
+    # 16 pair tiles on 74 CTA pairs: one wave either way, the half-size tile finishes in half the time
+    assert pk(1, 2048, 4) == "fa_fwd_kernel_pp"
+    # 400 pair tiles = 6 waves of 2 units; 800 half tiles = 11 waves of 1.05
+    assert pk(2, 4096, 25) == "fa_fwd_kernel_pp"
+    # 192 pair tiles = 3 waves (6 units); 384 half tiles = 6 waves (6.3 units)
+    assert pk(1, 8192, 12) == "fa_fwd_kernel_pair"
+    # an explicit mode wins over the rule
+    with _lib.thread_kernel_mode(1):
+        assert pk(1, 2048, 4) == "fa_fwd_kernel"
