@@ -18,7 +18,9 @@
 //   * two softmax warpgroups (one per Q tile, one thread per row, no shuffles): tcgen05.ld S,
 //     fp32 row max / exp2 / row sum in registers, P written back to TMEM as packed 16-bit in two
 //     parts (96 + 32 columns) so PV starts early, lazy rescale of O (only when the row max grew
-//     by more than 2^8), final 1/l scaling and TMA store of O through swizzled shared memory.
+//     by more than 2^8).
+//   * an epilogue warpgroup (generation 15): final 1/l scaling and TMA store of O through swizzled shared memory,
+//     off the softmax warpgroups' path -- they go straight from a tile's last block to the next tile's first.
 //
 // History (profiles/r01_*_notes.md, profiles/r02_pp_notes.md have the measurements behind each step; the
 // losing protocols are gone from this file, their patches are archived under profiles/):
@@ -36,9 +38,15 @@
 //       needing ~1400 clk of its own instruction time per KV block -- mbarrier waits at ~90 clk even when long
 //       complete, ~25-30 clk per tcgen05.mma, commits -- and in this kernel that time sits inside the serial
 //       chain through the shared S accumulator (pair kernel +2 % at seq_len >= 8192, single +10 % at 512).
+//   generation 15: the epilogue in its own warpgroup (512 threads, setmaxnreg 192 / 64 / 56).  A fit of tile time
+//       against block count had shown 1.5-3 us per work tile that was not block work (last PV -> read O -> convert
+//       -> store -> only then the next tile's first softmax): 1513 vs 1375 TFLOP/s at the headline on the same box.
+//       The TMA producer also asks for the next work tile's Q rows in L2.  What paces the kernel now, measured with
+//       -DFA_TRACE=1 cycle stamps: the serial chain through the shared S accumulator (profiles/r02_g15_notes.md).
 //   Removed after measurement: generation 4b (P aliased onto per-tile S, FlashAttention-4's layout: 1399 vs 1450),
 //   generation 8 (S prefetched into the exp2 shadow), generation 10 (S in 64-column halves), generation 11 (P
-//   through shared memory: 1422 vs 1464, shared-memory bandwidth).
+//   through shared memory: 1422 vs 1464, shared-memory bandwidth), generation 16 (PV_s(j) issued only behind
+//   S_s(j+1): noise), the softmax-side epilogue of generations 1-14 (r02_g14_softmax_side_epilogue_removed.patch).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -61,11 +69,7 @@ constexpr int kKVStages = FA_KV_STAGES;  // K/V ring slots of 32 KiB (a CTA pair
 constexpr int kMaxStages = 2 * kKVStages;
 constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
 constexpr int kHalfBytes = kTileBytes / 2;          // one TMA box: 128 rows x 64 cols (128 B rows)
-#ifndef FA_EPI_WG
-#define FA_EPI_WG 1           // generation 15: O / l -> 16 bit -> TMA store runs in its own (fourth) warpgroup
-#endif
-constexpr bool kEpiWG = FA_EPI_WG != 0;
-constexpr int kNumThreads = kEpiWG ? 512 : 384;     // 2 softmax warpgroups + control warpgroup (+ epilogue warpgroup)
+constexpr int kNumThreads = 512;                    // 2 softmax warpgroups + control warpgroup + epilogue warpgroup
 constexpr int kTmemCols = 512;
 
 constexpr int kSmemQ = 0;                                       // Q_0, Q_1
@@ -90,13 +94,13 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 #define FA_SPLIT_P 1          // 1: signal the MMA warp after 96 of 128 P columns, again after the rest
 #endif
 #ifndef FA_REGS_SOFTMAX
-#define FA_REGS_SOFTMAX (FA_EPI_WG ? 192 : 208)   // setmaxnreg for the softmax warpgroups ...
+#define FA_REGS_SOFTMAX 192   // setmaxnreg for the softmax warpgroups ...
 #endif
 #ifndef FA_REGS_CTRL
-#define FA_REGS_CTRL (FA_EPI_WG ? 64 : 88)        // ... the control warpgroup ...
+#define FA_REGS_CTRL 64       // ... the control warpgroup ...
 #endif
 #ifndef FA_REGS_EPI
-#define FA_REGS_EPI 56                            // ... and the epilogue warpgroup (reads O 32 columns at a time)
+#define FA_REGS_EPI 56        // ... and the epilogue warpgroup (reads O 32 columns at a time)
 #endif
 #ifndef FA_TRACE
 #define FA_TRACE 0            // 1: the production instantiations can record the cycle trace too (development builds)
@@ -107,9 +111,7 @@ static_assert(kSmemLaunchBytes <= 232448, "exceeds the 227 KiB opt-in shared mem
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr int kEmuPairsLast = FA_EMU_PAIRS_LAST;
 constexpr bool kSplitP = FA_SPLIT_P != 0;
-static_assert(kEpiWG ? (256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL + 128 * FA_REGS_EPI <= 512 * 128)
-                     : (256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL <= 384 * 168),
-              "register pool exceeded");
+static_assert(256 * FA_REGS_SOFTMAX + 128 * FA_REGS_CTRL + 128 * FA_REGS_EPI <= 512 * 128, "register pool exceeded");
 #ifndef FA_EXP_VARIANT
 #define FA_EXP_VARIANT 0      // code shape of exp_fragment (softmax_sm100.cuh)
 #endif
@@ -185,8 +187,6 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
     constexpr int kKHalfBytes = kPair ? kHalfBytes / 2 : kHalfBytes; // K: bytes per 64-d-column box
     constexpr uint32_t kArrivals = kPair ? 8u : 4u;  // softmax warps arriving on one barrier
     constexpr int kRowsPerTile = (kPair ? 2 : 1) * kQStages * kBlockM;
-    constexpr int kSmemO = kSmemStage;        // O staging of Q tile 0 ...
-    constexpr int kSmemOStride = kHalfBytes;  // ... and the step to tile 1
     auto col_s = [](int) -> uint32_t { return tmem_col_s(); };  // one S accumulator for both Q tiles
 
     // 1024-byte alignment (128B-swizzle atoms) is requested from the toolchain, which makes every
@@ -728,9 +728,9 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                     }
                         // P_s(j) overwrites P_s(j-1): PV_s(j-1) must have read it (issued about one
                     // softmax fragment ago, so this rarely spins)
-                    // (epilogue warpgroup: the first block of a tile overwrites the previous tile's last P_s too;
-                    // without it this warpgroup's own epilogue has waited for that PV)
-                    if (q == 0 && (kEpiWG ? g > 0 : j > 0)) {
+                    // (the first block of a tile overwrites the previous tile's last P_s too: generation 14's
+                    // epilogue inside this warpgroup used to wait for that PV)
+                    if (q == 0 && g > 0) {
                         if constexpr (kTr) {
                             if (tr) tr[5] = clk32();
                         }
@@ -762,78 +762,20 @@ __device__ __forceinline__ void fa_fwd_body(const CUtensorMap& tm_q, const CUten
                 l_run = l_run * alpha + ((sum_a.x + sum_a.y) + (sum_b.x + sum_b.y));
             }
 
-            // ------------------------------- epilogue ------------------------------------
-            if constexpr (kEpiWG) {
-                // generation 15: hand the row sum to the epilogue warpgroup and go straight on to the next tile
-                if (level >= 4) {
-                    if constexpr (kDebug) {
-                        if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0) {
-                            dbg.dump[2 * 128 * 128 + s * 128 + row] = l_run;
-                            dbg.dump[2 * 128 * 128 + 256 + s * 128 + row] = m_run;
-                        }
-                    }
-                    if (it > 0) named_bar_sync(12 + s, 256);  // the previous tile's row sum was read
-                    reinterpret_cast<float*>(smem_gen + kSmemL)[s * kBlockM + row] = l_run;
-                    named_bar_arrive(10 + s, 256);
-                }
-            } else if (level >= 4) {
-                wait(pv_done(s), (g - 1u) & 1u, 310 + s);  // last PV_s
-                tc_fence_after();
-                const float inv_l = 1.0f / l_run;
+            // generation 15: hand the row sum to the epilogue warpgroup and go straight on to the next tile
+            if (level >= 4) {
                 if constexpr (kDebug) {
                     if (dbg.dump != nullptr && blockIdx.x == 0 && it == 0) {
                         dbg.dump[2 * 128 * 128 + s * 128 + row] = l_run;
                         dbg.dump[2 * 128 * 128 + 256 + s * 128 + row] = m_run;
                     }
                 }
-                // O_s -> registers (all 128 columns), then hand the accumulator back to the MMA
-                // warp so the next tile's first PV_s can proceed while we convert and store.
-                uint32_t o[4][32];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) tmem_ld_32x32b_x32(t_o + q * 32, o[q]);
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive_leader(o_free(s));
-                // Two passes of 64 columns (= one TMA box) through this warpgroup's 16 KiB staging
-                // buffer, written with the TMA 128B swizzle: 16-byte chunk c of row r lives at
-                // chunk (c ^ (r & 7)) of that row.
-                const TileCoord tc = coord_of(tile);
-                uint8_t* stage_row = smem_gen + kSmemO + s * kSmemOStride + row * 128;
-                const uint32_t stage_u32 = smem_base + kSmemO + s * kSmemOStride;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int qq = 0; qq < 2; ++qq) {
-                        const int q = 2 * h + qq;
-#pragma unroll
-                        for (int cidx = 0; cidx < 4; ++cidx) {
-                            uint4 v;
-                            v.x = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 0]) * inv_l,
-                                                   __uint_as_float(o[q][cidx * 8 + 1]) * inv_l);
-                            v.y = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 2]) * inv_l,
-                                                   __uint_as_float(o[q][cidx * 8 + 3]) * inv_l);
-                            v.z = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 4]) * inv_l,
-                                                   __uint_as_float(o[q][cidx * 8 + 5]) * inv_l);
-                            v.w = pack_16x2<kBF16>(__uint_as_float(o[q][cidx * 8 + 6]) * inv_l,
-                                                   __uint_as_float(o[q][cidx * 8 + 7]) * inv_l);
-                            const int chunk = (qq * 4 + cidx) ^ (row & 7);
-                            *reinterpret_cast<uint4*>(stage_row + chunk * 16) = v;
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + s, 128);
-                    if (row == 0) {
-                        tma_store_4d(&tm_o, stage_u32, 64 * h, tc.head, tc.q_row0 + s * kBlockM,
-                                     tc.batch);
-                        tma_store_commit();
-                        tma_store_wait_read<0>();  // staging buffer reusable
-                    }
-                    named_bar_sync(1 + s, 128);
-                }
+                if (it > 0) named_bar_sync(12 + s, 256);  // the previous tile's row sum was read
+                reinterpret_cast<float*>(smem_gen + kSmemL)[s * kBlockM + row] = l_run;
+                named_bar_arrive(10 + s, 256);
             }
         }
-    } else if constexpr (kEpiWG) {
+    } else {
         // =================================== epilogue (generation 15) =====================================
         // Own warpgroup (as in the ping-pong kernel): O_s / l -> 16 bit -> swizzled shared memory -> TMA store, for
         // Q tile 0 then Q tile 1 of every work tile.  With the epilogue inside the softmax warpgroups a tile boundary

@@ -35,7 +35,6 @@ VARIANTS = {
     "ppexpv1": {"FA_EXP_VARIANT": 1},
     "hint": {"FA_WAIT_HINT": 10000000},   # CUTLASS-style 10 ms suspend-time hint on every try_wait
     "sleep32": {"FA_WAIT_SLEEP": 32},     # nanosleep back-off in the wait loops
-    "noepi": {"FA_EPI_WG": 0},            # generation 14: epilogue inside the softmax warpgroups (384 threads)
     "kvpf": {"FA_Q_PREFETCH": 2},         # ... plus the next tile's first two K/V blocks when (batch, head) changes
     "r200": {"FA_REGS_SOFTMAX": 200, "FA_REGS_CTRL": 56, "FA_REGS_EPI": 56},
     "trace": {"FA_TRACE": 1},             # production instantiations record the cycle trace (tools/gpu_trace2.py)
