@@ -14,7 +14,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libfa_sm100.so"
 SOURCES = [CSRC / "fa_api.cu"]
-HEADERS = [CSRC / "fa_fwd_sm100.cuh", CSRC / "ptx_sm100.cuh", CSRC / "softmax_sm100.cuh",
+HEADERS = [CSRC / "fa_fwd_sm100.cuh", CSRC / "fa_fwd_pp_sm100.cuh", CSRC / "ptx_sm100.cuh", CSRC / "softmax_sm100.cuh",
            CSRC.parent.parent / "include" / "fa_sm100.h"]
 
 NVCC_FLAGS = [
