@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Extracts the metrics we track from an .ncu-rep (read on the CPU box with `ncu -i`) into a small
-JSON + text summary under profiles/.  Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep r01_v2"""
+JSON + text summary under profiles/.  Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep r01_v2 [--headline]
+(--headline also rewrites profiles/ncu_summary.json, which bench.py reads for roofline.traffic)"""
 import csv
 import io
 import json
@@ -69,8 +70,9 @@ def main():
             summ["dram_bytes_err"] = str(e)
     (ROOT / "profiles").mkdir(exist_ok=True)
     (ROOT / "profiles" / f"{tag}_ncu_summary.json").write_text(json.dumps(summ, indent=1))
-    (ROOT / "profiles" / "ncu_summary.json").write_text(json.dumps(
-        {"tag": tag, "dram_bytes_per_launch": summ.get("dram_bytes_per_launch")}, indent=1))
+    if "--headline" in sys.argv:  # only the headline capture feeds bench.py's roofline.traffic
+        (ROOT / "profiles" / "ncu_summary.json").write_text(json.dumps(
+            {"tag": tag, "dram_bytes_per_launch": summ.get("dram_bytes_per_launch")}, indent=1))
     for k in kernels:
         for kk, vv in k.items():
             print(f"{kk:90s} {vv}")
