@@ -145,9 +145,9 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                # an NVML call costs about a millisecond and the power reading is a ~1 s average anyway: in the fast
-                # sampler (short timed regions) read it every fourth time only
-                if self.period >= 0.005 or n % 4 == 0:
+                # an NVML call costs about a millisecond and the power reading is a ~1 s average: the fast sampler
+                # (short timed regions) reads clocks and throttle reasons only
+                if self.period >= 0.005:
                     self.power_mw.append(nv.nvmlDeviceGetPowerUsage(self.h))
                 n += 1
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -164,7 +164,8 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         out = {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                "samples": len(s)}
-        if self.power_mw:
+        if self.power_mw and self.period >= 0.005:
+            # (NVML's power reading is a ~1 s average: only the >= 2 s `sustained` region reports it)
             out["power_w_max"] = max(self.power_mw) / 1000.0
             out["power_w_mean"] = sum(self.power_mw) / len(self.power_mw) / 1000.0
         return out
